@@ -1,0 +1,161 @@
+/*
+ * rfa_b200.h -- C ABI of librfa_b200.so, the B200 (sm_100a) implementation of
+ * RF Analyzer's IQ->spectrum and IQ->audio hot path.
+ *
+ * Plain pointers and sizes only; every function returns an int status (RFA_OK == 0)
+ * and rfa_last_error() describes the last failure on the calling thread.  There is no
+ * CPU fallback: without a CUDA device every compute entry point fails with RFA_ERR_CUDA.
+ *
+ * Each entry point names the reference interface it replaces.  Paths are relative to the
+ * reference tree; A/ = app/src/main/java/com/mantz_it/rfanalyzer/.
+ *
+ * Memory: every data pointer of a call lives in ONE space, given by `mem`:
+ *   RFA_MEM_HOST   -- host memory; the library stages H2D/D2H copies on the context's
+ *                     stream and the call returns when the results are in the buffers.
+ *   RFA_MEM_DEVICE -- device memory of the context's GPU; the call is asynchronous on
+ *                     the context's stream (use rfa_ctx_sync or your own stream sync).
+ * Sample buffers must be naturally aligned for their element (2 B for 8-bit IQ pairs,
+ * 4 B for 16-bit IQ pairs and floats, 8 B for interleaved complex float).
+ */
+#ifndef RFA_B200_H
+#define RFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFA_VERSION 100
+
+enum { RFA_OK = 0, RFA_ERR_INVALID = 1, RFA_ERR_CUDA = 2, RFA_ERR_UNSUPPORTED = 3, RFA_ERR_NOMEM = 4 };
+enum { RFA_MEM_HOST = 0, RFA_MEM_DEVICE = 1 };
+
+/* IQ sample formats = the three IQConverter subclasses
+ * (A/source/Signed8BitIQConverter.java, Unsigned8BitIQConverter.java, Signed16BitIQConverter.kt) */
+enum { RFA_FMT_S8 = 0, RFA_FMT_U8 = 1, RFA_FMT_S16LE = 2 };
+
+/* FFT windows. BLACKMAN_REF is the only one the reference has
+ * (nativedsp/src/main/java/com/mantz_it/nativedsp/NativeDsp.kt:14-21). */
+enum { RFA_WIN_BLACKMAN_REF = 0, RFA_WIN_HANN = 1, RFA_WIN_RECT = 2 };
+
+/* tap-design windows of A/dsp/WindowFunctions.kt:44-100 */
+enum { RFA_TAPWIN_BLACKMAN = 0, RFA_TAPWIN_HAMMING = 1, RFA_TAPWIN_KAISER = 2 };
+
+/* A/ui/composable/DemodulationTab.kt:90-99 (ordinal order) */
+enum { RFA_MODE_OFF = 0, RFA_MODE_AM, RFA_MODE_NFM, RFA_MODE_WFM, RFA_MODE_LSB, RFA_MODE_USB, RFA_MODE_CW };
+
+/* flags for the FIR / resampler / demodulator kernels */
+enum {
+    RFA_SUM_FMA = 0,   /* fused multiply-add accumulation: fastest, within 1e-6 relative of the reference */
+    RFA_SUM_EXACT = 1  /* multiply and add rounded separately, in the reference's tap order: bit-exact */
+};
+
+typedef struct rfa_ctx rfa_ctx;
+typedef struct rfa_spectrum_plan rfa_spectrum_plan;
+typedef struct rfa_fir rfa_fir;
+typedef struct rfa_resampler rfa_resampler;
+typedef struct rfa_chain rfa_chain;
+
+/* ---- library / context --------------------------------------------------------------- */
+int rfa_version(void);
+const char *rfa_last_error(void);
+/* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one */
+int rfa_ctx_create(int device, void *stream, rfa_ctx **out);
+int rfa_ctx_destroy(rfa_ctx *ctx);
+int rfa_ctx_sync(rfa_ctx *ctx);
+int rfa_ctx_device(const rfa_ctx *ctx);
+int rfa_ctx_sm_count(const rfa_ctx *ctx);
+void *rfa_ctx_stream(const rfa_ctx *ctx);
+/* number of kernels this context has launched (bench.py's gpu_launches) */
+long long rfa_ctx_launch_count(const rfa_ctx *ctx);
+/* pinned host memory, so RFA_MEM_HOST calls copy at full PCIe rate and overlap */
+int rfa_host_alloc(size_t bytes, void **out);
+int rfa_host_free(void *p);
+
+/* ---- IQ conversion: IQConverter.fillPacketIntoSamplePacket --------------------------- */
+/* A/source/Signed8BitIQConverter.java:80-99, Unsigned8BitIQConverter.java:80-99,
+ * Signed16BitIQConverter.kt:89-124.  iq: nsamples interleaved I,Q pairs -> planar re, im.
+ * Bit-exact with the reference's look-up tables. */
+int rfa_convert(rfa_ctx *ctx, int fmt, const void *iq, long long nsamples, float *re, float *im, int mem);
+
+/* ---- NCO mixer: IQConverter.mixPacketIntoSamplePacket -------------------------------- */
+/* Host-side table design = generateMixerLookupTable + calcOptimalCosineLength
+ * (A/source/IQConverter.java:64-76, Signed8BitIQConverter.java:54-77,
+ * Signed16BitIQConverter.kt:59-87).  mix_frequency = (int)(source - channel frequency).
+ * Writes the effective frequency (after the "+= sampleRate" rule), the table length
+ * (<= 500) and cos/sin tables of that length (capacity >= 500 floats each). */
+int rfa_nco_design(int fmt, int sample_rate, int mix_frequency, int *effective_frequency, int *length,
+                   float *cos_table, float *sin_table);
+/* re = v(I)*cos - v(Q)*sin, im = v(Q)*cos + v(I)*sin with every product rounded to float
+ * first (the reference's 2-D product tables); sample n uses table index
+ * (nco_index + n) % nco_length.  cos/sin tables are HOST pointers in both modes. */
+int rfa_mix(rfa_ctx *ctx, int fmt, const void *iq, long long nsamples, const float *cos_table,
+            const float *sin_table, int nco_length, int nco_index, float *re, float *im, int mem);
+
+/* ---- NativeDsp ------------------------------------------------------------------------ */
+/* NativeDsp.makeWindow (NativeDsp.kt:14-21) and variants; host function. */
+int rfa_make_window(int window, int n, float *out);
+/* Java_com_mantz_1it_nativedsp_NativeDsp_performFFT (nativedsp/src/main/cpp/nativedsp.cpp:19-42):
+ * ordered forward complex FFT, interleaved float32, unnormalised; `batch` transforms. */
+int rfa_fft_c2c(rfa_ctx *ctx, const float *in, float *out, int n, long long batch, int mem);
+/* Java_..._performFFTAndLogMag (nativedsp.cpp:44-81): FFT, 10*log10(|X|/n), fft-shifted. */
+int rfa_fft_logmag(rfa_ctx *ctx, const float *in, float *mag, int n, long long batch, int mem);
+/* NativeDsp.performWindowedFftAndReturnMag (NativeDsp.kt:43-62): planar re/im in, dB out. */
+int rfa_windowed_fft_logmag(rfa_ctx *ctx, const float *re, const float *im, float *mag, int n,
+                            long long batch, int window, int mem);
+
+/* ---- fused spectrum path --------------------------------------------------------------
+ * Scheduler.kt:266 (fill) + NativeDsp.kt:43-62 + nativedsp.cpp:44-81 +
+ * FftProcessor.kt:224-245 (row store, peak hold) + AnalyzerSurface.kt:710-714 (time average)
+ * in one pass over the IQ bytes. */
+typedef struct {
+    int format;    /* RFA_FMT_* */
+    int fft_size;  /* power of two, 16 .. 65536 (the app offers 1024 .. 65536, DisplayTab.kt:108-111) */
+    int window;    /* RFA_WIN_* */
+    int avg_len;   /* L = fftAverageLength, 0 .. 30: the average spans the newest L+1 rows */
+    int peak_hold; /* FftProcessor.fftPeakHold */
+} rfa_spectrum_desc;
+
+typedef struct {
+    float *rows;          /* dB rows, or NULL to skip the waterfall store */
+    long long row0;       /* frame f goes to row (row0 + f*row_step) mod ring_rows           */
+    long long row_step;   /* +1: linear [frames][n]; -1: the reference's backwards ring      */
+    long long ring_rows;  /* 0 = no wrap (linear); 300/400/500 = FftProcessor.kt:104 rings   */
+    long long row_stride; /* floats between rows (>= fft_size)                                */
+    long long history_rows; /* ring only: rows already valid before this call (for avg)      */
+    float *peaks;         /* [n] running element-wise max of all rows, or NULL               */
+    int peaks_accumulate; /* 1: continue from the values in `peaks`; 0: restart at -999999f  */
+    float *avg;           /* [n] mean of the newest avg_len+1 rows, or NULL                  */
+} rfa_spectrum_out;
+
+int rfa_spectrum_plan_create(rfa_ctx *ctx, const rfa_spectrum_desc *desc, rfa_spectrum_plan **out);
+int rfa_spectrum_plan_destroy(rfa_spectrum_plan *plan);
+/* iq: nframes * fft_size samples, frames contiguous and non-overlapping (Scheduler.kt:254-276). */
+int rfa_spectrum_process(rfa_spectrum_plan *plan, const void *iq, long long nframes,
+                         const rfa_spectrum_out *out, int mem);
+/* algorithmic HBM bytes of one process call: nframes*n*(bytes_in + 4) + 8*n */
+long long rfa_spectrum_algorithmic_bytes(const rfa_spectrum_plan *plan, long long nframes, int rows_stored);
+
+/* ---- reductions over waterfall rows ---------------------------------------------------- */
+/* AnalyzerSurface.kt:683-684,710-714: avg = (sum of rows newest, newest+dir, ... L+1 terms,
+ * summed in that order in float32) / (L+1); terms past `valid` count as -9999f. */
+int rfa_average_rows(rfa_ctx *ctx, const float *rows, long long newest, long long dir, long long ring_rows,
+                     long long row_stride, long long valid, int avg_len, int n, float *avg, int mem_rows,
+                     int mem_avg);
+/* FftProcessor.kt:143-157: host helper for the channel's bin range ... */
+int rfa_channel_bins(int n, long long frequency, int sample_rate, long long chan_start, long long chan_end,
+                     int *bin_start, int *bin_end);
+/* ... and the mean dB over [bin_start, bin_end) of nrows rows (device rows, `out` per mem_out). */
+int rfa_channel_strength(rfa_ctx *ctx, const float *rows, long long row0, long long row_step,
+                         long long ring_rows, long long row_stride, long long nrows, int bin_start,
+                         int bin_end, float *out, int mem_out);
+/* FftProcessor.kt:199-217: shift `nrows` device rows by `shift` bins, fill with -9999f. */
+int rfa_shift_rows(rfa_ctx *ctx, float *rows, long long nrows, long long row_stride, int n, int shift);
+int rfa_fill(rfa_ctx *ctx, float *dst, long long count, float value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFA_B200_H */

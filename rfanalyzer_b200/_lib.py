@@ -1,0 +1,111 @@
+"""ctypes binding of librfa_b200.so (the C ABI declared in include/rfa_b200.h).
+
+There is no fallback of any kind: if the shared library is missing, or a call fails
+(for instance because no B200 is present), an exception is raised.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "librfa_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = range(5)
+MEM_HOST, MEM_DEVICE = 0, 1
+FMT_S8, FMT_U8, FMT_S16LE = 0, 1, 2
+WIN_BLACKMAN_REF, WIN_HANN, WIN_RECT = 0, 1, 2
+TAPWIN_BLACKMAN, TAPWIN_HAMMING, TAPWIN_KAISER = 0, 1, 2
+MODE_OFF, MODE_AM, MODE_NFM, MODE_WFM, MODE_LSB, MODE_USB, MODE_CW = range(7)
+SUM_FMA, SUM_EXACT = 0, 1
+BYTES_PER_SAMPLE = {FMT_S8: 2, FMT_U8: 2, FMT_S16LE: 4}
+
+
+class RfaError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"librfa_b200 error {code}: {message}")
+        self.code = code
+
+
+class SpectrumDesc(C.Structure):
+    _fields_ = [("format", C.c_int), ("fft_size", C.c_int), ("window", C.c_int), ("avg_len", C.c_int),
+                ("peak_hold", C.c_int)]
+
+
+class SpectrumOut(C.Structure):
+    _fields_ = [("rows", C.c_void_p), ("row0", C.c_longlong), ("row_step", C.c_longlong),
+                ("ring_rows", C.c_longlong), ("row_stride", C.c_longlong), ("history_rows", C.c_longlong),
+                ("peaks", C.c_void_p), ("peaks_accumulate", C.c_int), ("avg", C.c_void_p)]
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [("format", C.c_int), ("sample_rate", C.c_int), ("source_frequency", C.c_longlong),
+                ("channel_frequency", C.c_longlong), ("mode", C.c_int), ("channel_width", C.c_int),
+                ("packet_samples", C.c_int), ("volume", C.c_float), ("flags", C.c_int)]
+
+
+_vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+_pi, _pll, _pvp = C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); every function include/rfa_b200.h declares is listed here and
+# tests/test_abi.py checks the two stay in step.
+SIGNATURES = {
+    "rfa_version": (_i, []),
+    "rfa_last_error": (C.c_char_p, []),
+    "rfa_ctx_create": (_i, [_i, _vp, _pvp]),
+    "rfa_ctx_destroy": (_i, [_vp]),
+    "rfa_ctx_sync": (_i, [_vp]),
+    "rfa_ctx_device": (_i, [_vp]),
+    "rfa_ctx_sm_count": (_i, [_vp]),
+    "rfa_ctx_stream": (_vp, [_vp]),
+    "rfa_ctx_launch_count": (_ll, [_vp]),
+    "rfa_host_alloc": (_i, [C.c_size_t, _pvp]),
+    "rfa_host_free": (_i, [_vp]),
+    "rfa_convert": (_i, [_vp, _i, _vp, _ll, _vp, _vp, _i]),
+    "rfa_nco_design": (_i, [_i, _i, _i, _pi, _pi, _vp, _vp]),
+    "rfa_mix": (_i, [_vp, _i, _vp, _ll, _vp, _vp, _i, _i, _vp, _vp, _i]),
+    "rfa_make_window": (_i, [_i, _i, _vp]),
+    "rfa_fft_c2c": (_i, [_vp, _vp, _vp, _i, _ll, _i]),
+    "rfa_fft_logmag": (_i, [_vp, _vp, _vp, _i, _ll, _i]),
+    "rfa_windowed_fft_logmag": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i]),
+    "rfa_spectrum_plan_create": (_i, [_vp, C.POINTER(SpectrumDesc), _pvp]),
+    "rfa_spectrum_plan_destroy": (_i, [_vp]),
+    "rfa_spectrum_process": (_i, [_vp, _vp, _ll, C.POINTER(SpectrumOut), _i]),
+    "rfa_spectrum_algorithmic_bytes": (_ll, [_vp, _ll, _i]),
+    "rfa_average_rows": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _vp, _i, _i]),
+    "rfa_channel_bins": (_i, [_i, _ll, _i, _ll, _ll, _pi, _pi]),
+    "rfa_channel_strength": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _vp, _i]),
+    "rfa_shift_rows": (_i, [_vp, _vp, _ll, _ll, _i, _i]),
+    "rfa_fill": (_i, [_vp, _vp, _ll, _f]),
+}
+
+_LIB = None
+
+
+def load():
+    """Load librfa_b200.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RfaError(-1, f"{LIB_PATH} is missing: build it with `make -C rfanalyzer_b200/csrc` "
+                               "(there is no fallback implementation)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = lib
+    return _LIB
+
+
+def check(rc):
+    if rc != OK:
+        raise RfaError(rc, load().rfa_last_error().decode("utf-8", "replace"))
+
+
+def ptr(x):
+    """Address of a torch tensor, numpy array, int or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return x.ctypes.data

@@ -1,0 +1,652 @@
+// capi.cu -- context, conversion, NativeDsp-level and fused-spectrum entry points of the
+// C ABI (include/rfa_b200.h).  Thin: argument checks, table caches, staging for host
+// buffers, then a kernel launch on the context's stream.
+#include <cstring>
+
+#include "capi_core.h"
+#include "host_design.h"
+#include "kernels.h"
+#include "rfa_tables.h"
+#include "spectrum_launch.h"
+
+namespace rfa {
+
+static thread_local std::string g_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return RFA_ERR_CUDA;
+}
+
+int Buf::ensure(size_t bytes) {
+    if (bytes <= cap) return RFA_OK;
+    release();
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        cap = 0;
+        set_error("out of %s memory allocating %zu bytes (%s)", pinned ? "pinned host" : "device", want,
+                  cudaGetErrorString(e));
+        cudaGetLastError();
+        return RFA_ERR_NOMEM;
+    }
+    cap = want;
+    return RFA_OK;
+}
+
+void Buf::release() {
+    if (p) {
+        if (pinned)
+            cudaFreeHost(p);
+        else
+            cudaFree(p);
+    }
+    p = nullptr;
+    cap = 0;
+}
+
+static int fmt_bytes(int fmt) { return fmt == RFA_FMT_S16LE ? 4 : 2; }
+static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+}  // namespace rfa
+
+using namespace rfa;
+
+int rfa_ctx::use() {
+    RFA_CK(cudaSetDevice(device));
+    return RFA_OK;
+}
+
+int rfa_ctx::get_twiddles(int n, const cf **out) {
+    auto it = twiddles.find(n);
+    if (it == twiddles.end()) {
+        // n > 0: per-pass Stockham tables of an n-point transform; n < 0: plain exp(-2*pi*i*t/|n|)
+        std::vector<cf> host;
+        if (n > 0) {
+            host = make_pass_twiddles(n);
+        } else {
+            host.resize((size_t)-n);
+            make_twiddles(-n, host.data());
+        }
+        cf *dev = nullptr;
+        RFA_CK(cudaMalloc(&dev, sizeof(cf) * host.size()));
+        RFA_CK(cudaMemcpyAsync(dev, host.data(), sizeof(cf) * host.size(), cudaMemcpyHostToDevice, stream));
+        RFA_CK(cudaStreamSynchronize(stream));
+        it = twiddles.emplace(n, dev).first;
+    }
+    *out = it->second;
+    return RFA_OK;
+}
+
+int rfa_ctx::get_window(int kind, int n, const float **out) {
+    auto key = std::make_pair(kind, n);
+    auto it = windows.find(key);
+    if (it == windows.end()) {
+        std::vector<float> host((size_t)n);
+        make_window(kind, n, host.data());
+        float *dev = nullptr;
+        RFA_CK(cudaMalloc(&dev, sizeof(float) * (size_t)n));
+        RFA_CK(cudaMemcpyAsync(dev, host.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, stream));
+        RFA_CK(cudaStreamSynchronize(stream));
+        it = windows.emplace(key, dev).first;
+    }
+    *out = it->second;
+    return RFA_OK;
+}
+
+extern "C" {
+
+int rfa_version(void) { return RFA_VERSION; }
+const char *rfa_last_error(void) { return g_error.c_str(); }
+
+int rfa_ctx_create(int device, void *stream, rfa_ctx **out) {
+    RFA_REQUIRE(out != nullptr, "rfa_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); librfa_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return RFA_ERR_CUDA;
+    }
+    RFA_REQUIRE(device >= 0 && device < count, "rfa_ctx_create: device %d out of range (0..%d)", device, count - 1);
+    RFA_CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RFA_CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return RFA_ERR_UNSUPPORTED;
+    }
+    rfa_ctx *c = new rfa_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        RFA_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    RFA_CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    RFA_CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        RFA_CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        RFA_CK(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+        RFA_CK(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return RFA_OK;
+}
+
+int rfa_ctx_destroy(rfa_ctx *c) {
+    if (!c) return RFA_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->twiddles) cudaFree(kv.second);
+    for (auto &kv : c->windows) cudaFree(kv.second);
+    for (auto &b : c->stage) b.release();
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(c->ev_in[i]);
+        cudaEventDestroy(c->ev_k[i]);
+        cudaEventDestroy(c->ev_out[i]);
+    }
+    cudaStreamDestroy(c->s_in);
+    cudaStreamDestroy(c->s_out);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RFA_OK;
+}
+
+int rfa_ctx_sync(rfa_ctx *c) {
+    RFA_REQUIRE(c != nullptr, "rfa_ctx_sync: ctx is NULL");
+    RFA_CK(cudaStreamSynchronize(c->stream));
+    return RFA_OK;
+}
+int rfa_ctx_device(const rfa_ctx *c) { return c ? c->device : -1; }
+int rfa_ctx_sm_count(const rfa_ctx *c) { return c ? c->num_sms : 0; }
+void *rfa_ctx_stream(const rfa_ctx *c) { return c ? (void *)c->stream : nullptr; }
+long long rfa_ctx_launch_count(const rfa_ctx *c) { return c ? c->launches : 0; }
+
+int rfa_host_alloc(size_t bytes, void **out) {
+    RFA_REQUIRE(out != nullptr, "rfa_host_alloc: out is NULL");
+    RFA_CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return RFA_OK;
+}
+int rfa_host_free(void *p) {
+    if (p) RFA_CK(cudaFreeHost(p));
+    return RFA_OK;
+}
+
+/* ---------------------------------------------------------------- convert / mix ---- */
+static int convert_or_mix(rfa_ctx *c, int fmt, const void *iq, long long n, const float *cosT, const float *sinT,
+                          int ncoLen, int ncoIdx, float *re, float *im, int mem, bool mix) {
+    RFA_REQUIRE(c != nullptr, "ctx is NULL");
+    RFA_REQUIRE(fmt >= RFA_FMT_S8 && fmt <= RFA_FMT_S16LE, "unknown sample format %d", fmt);
+    RFA_REQUIRE(n >= 0, "negative sample count");
+    if (n == 0) return RFA_OK;
+    RFA_REQUIRE(iq && re && im, "NULL buffer");
+    if (int rc = c->use()) return rc;
+    const size_t in_bytes = (size_t)n * fmt_bytes(fmt), out_bytes = (size_t)n * sizeof(float);
+    const float *dc = nullptr, *ds = nullptr;
+    if (mix) {
+        RFA_REQUIRE(cosT && sinT, "NULL NCO table");
+        RFA_REQUIRE(ncoLen >= 1 && ncoLen <= 500, "NCO table length %d outside 1..500", ncoLen);
+        RFA_REQUIRE(ncoIdx >= 0 && ncoIdx < ncoLen, "NCO index %d outside table", ncoIdx);
+        if (int rc = c->stage[3].ensure(sizeof(float) * 1024)) return rc;
+        float *t = c->stage[3].as<float>();
+        RFA_CK(cudaMemcpyAsync(t, cosT, sizeof(float) * ncoLen, cudaMemcpyHostToDevice, c->stream));
+        RFA_CK(cudaMemcpyAsync(t + 512, sinT, sizeof(float) * ncoLen, cudaMemcpyHostToDevice, c->stream));
+        dc = t;
+        ds = t + 512;
+    }
+    const void *din = iq;
+    float *dre = re, *dim = im;
+    if (mem == RFA_MEM_HOST) {
+        if (int rc = c->stage[0].ensure(in_bytes)) return rc;
+        if (int rc = c->stage[1].ensure(out_bytes)) return rc;
+        if (int rc = c->stage[2].ensure(out_bytes)) return rc;
+        RFA_CK(cudaMemcpyAsync(c->stage[0].p, iq, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        din = c->stage[0].p;
+        dre = c->stage[1].as<float>();
+        dim = c->stage[2].as<float>();
+    } else {
+        RFA_REQUIRE(((uintptr_t)iq % (fmt == RFA_FMT_S16LE ? 4 : 2)) == 0, "iq pointer misaligned for its format");
+    }
+    cudaError_t e = mix ? mix_launch(fmt, din, n, dre, dim, dc, ds, ncoLen, ncoIdx, c->num_sms, c->stream)
+                        : convert_launch(fmt, din, n, dre, dim, c->num_sms, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, mix ? "mix kernel" : "convert kernel");
+    c->launches++;
+    if (mem == RFA_MEM_HOST) {
+        RFA_CK(cudaMemcpyAsync(re, dre, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        RFA_CK(cudaMemcpyAsync(im, dim, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    } else if (mix) {
+        // the NCO tables were staged from host memory the caller may reuse right away
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    }
+    return RFA_OK;
+}
+
+int rfa_convert(rfa_ctx *c, int fmt, const void *iq, long long n, float *re, float *im, int mem) {
+    return convert_or_mix(c, fmt, iq, n, nullptr, nullptr, 0, 0, re, im, mem, false);
+}
+
+int rfa_nco_design(int fmt, int sample_rate, int mix_frequency, int *effective_frequency, int *length,
+                   float *cos_table, float *sin_table) {
+    RFA_REQUIRE(fmt >= RFA_FMT_S8 && fmt <= RFA_FMT_S16LE, "unknown sample format %d", fmt);
+    RFA_REQUIRE(sample_rate > 0, "sample rate must be positive");
+    RFA_REQUIRE(length && cos_table && sin_table, "NULL output");
+    std::vector<float> c, s;
+    int eff = 0;
+    design::nco_tables(fmt, sample_rate, mix_frequency, &eff, &c, &s);
+    RFA_REQUIRE(c.size() <= 500, "NCO table of %zu entries exceeds the reference's 500", c.size());
+    if (effective_frequency) *effective_frequency = eff;
+    *length = (int)c.size();
+    memcpy(cos_table, c.data(), sizeof(float) * c.size());
+    memcpy(sin_table, s.data(), sizeof(float) * s.size());
+    return RFA_OK;
+}
+
+int rfa_mix(rfa_ctx *c, int fmt, const void *iq, long long n, const float *cosT, const float *sinT, int ncoLen,
+            int ncoIdx, float *re, float *im, int mem) {
+    return convert_or_mix(c, fmt, iq, n, cosT, sinT, ncoLen, ncoIdx, re, im, mem, true);
+}
+
+/* ---------------------------------------------------------------- NativeDsp level ---- */
+int rfa_make_window(int window, int n, float *out) {
+    RFA_REQUIRE(window >= RFA_WIN_BLACKMAN_REF && window <= RFA_WIN_RECT, "unknown window %d", window);
+    RFA_REQUIRE(n > 0 && out, "bad window request");
+    make_window(window, n, out);
+    return RFA_OK;
+}
+
+// in_kind: FMT_CF32 (interleaved) or FMT_PF32 (planar); out_kind: OUT_DB / OUT_CPLX
+static int fft_generic(rfa_ctx *c, int in_kind, int out_kind, const float *in_a, const float *in_b, float *out,
+                       int n, long long batch, int window, int mem) {
+    RFA_REQUIRE(c != nullptr, "ctx is NULL");
+    RFA_REQUIRE(is_pow2(n) && n >= 16 && n <= 65536,
+                "FFT size %d unsupported: need a power of two in 16..65536", n);
+    RFA_REQUIRE(batch >= 0, "negative batch");
+    if (batch == 0) return RFA_OK;
+    RFA_REQUIRE(in_a && out && (in_kind != FMT_PF32 || in_b), "NULL buffer");
+    if (int rc = c->use()) return rc;
+    const size_t total = (size_t)batch * (size_t)n;
+    const size_t in_floats = in_kind == FMT_CF32 ? 2 * total : total;
+    const size_t out_floats = out_kind == OUT_CPLX ? 2 * total : total;
+    SpectrumLaunch L{};
+    L.N = n;
+    L.in_fmt = in_kind;
+    L.out_kind = out_kind;
+    L.stream = c->stream;
+    L.num_sms = c->num_sms;
+    const int nl = n > 16384 ? 16384 : n;
+    if (int rc = c->get_twiddles(nl, &L.p.tw)) return rc;
+    if (n > 16384)
+        if (int rc = c->get_twiddles(-n, &L.p.twN)) return rc;
+    if (window >= 0)
+        if (int rc = c->get_window(window, n, &L.p.win)) return rc;
+    const float *da = in_a, *db = in_b;
+    float *dout = out;
+    if (mem == RFA_MEM_HOST) {
+        if (int rc = c->stage[0].ensure(in_floats * sizeof(float))) return rc;
+        if (int rc = c->stage[1].ensure(out_floats * sizeof(float))) return rc;
+        RFA_CK(cudaMemcpyAsync(c->stage[0].p, in_a, in_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        da = c->stage[0].as<float>();
+        if (in_kind == FMT_PF32) {
+            if (int rc = c->stage[2].ensure(total * sizeof(float))) return rc;
+            RFA_CK(cudaMemcpyAsync(c->stage[2].p, in_b, total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            db = c->stage[2].as<float>();
+        }
+        dout = c->stage[1].as<float>();
+    }
+    L.p.in = da;
+    L.p.in_im = db;
+    L.p.rows = dout;
+    L.p.row0 = 0;
+    L.p.row_step = 1;
+    L.p.ring_rows = 0;
+    L.p.row_stride = out_kind == OUT_CPLX ? 2LL * n : n;
+    L.p.nframes = batch;
+    L.p.store_from = 0;
+    L.p.inv_n2 = 1.0f / ((float)n * (float)n);
+    cudaError_t e = spectrum_launch(L);
+    if (e != cudaSuccess) return cuda_fail(e, "spectrum kernel");
+    c->launches++;
+    if (mem == RFA_MEM_HOST) {
+        RFA_CK(cudaMemcpyAsync(out, dout, out_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    }
+    return RFA_OK;
+}
+
+int rfa_fft_c2c(rfa_ctx *c, const float *in, float *out, int n, long long batch, int mem) {
+    return fft_generic(c, FMT_CF32, OUT_CPLX, in, nullptr, out, n, batch, -1, mem);
+}
+int rfa_fft_logmag(rfa_ctx *c, const float *in, float *mag, int n, long long batch, int mem) {
+    return fft_generic(c, FMT_CF32, OUT_DB, in, nullptr, mag, n, batch, -1, mem);
+}
+int rfa_windowed_fft_logmag(rfa_ctx *c, const float *re, const float *im, float *mag, int n, long long batch,
+                            int window, int mem) {
+    RFA_REQUIRE(window >= RFA_WIN_BLACKMAN_REF && window <= RFA_WIN_RECT, "unknown window %d", window);
+    return fft_generic(c, FMT_PF32, OUT_DB, re, im, mag, n, batch, window, mem);
+}
+
+/* ---------------------------------------------------------------- fused spectrum ---- */
+}  // extern "C"
+
+struct rfa_spectrum_plan {
+    rfa_ctx *ctx;
+    rfa_spectrum_desc d;
+    const cf *tw = nullptr, *twN = nullptr;
+    const float *win = nullptr;
+    Buf ticket;     // finished-tail-row counters of the fused kernel
+    Buf tail;       // (L+1) rows when the caller stores no rows
+    Buf dpeaks;     // device running peaks (host mode)
+    Buf davg;       // device average (host mode)
+    Buf din[2], drows[2];  // pipelined host mode
+};
+
+// avg request of one launch (device pointer + which rows hold data)
+struct AvgReq {
+    float *avg = nullptr;
+    long long valid = 0;
+};
+
+// one device-resident batch = ONE kernel launch (plus a fill when the peaks restart).
+// `peaks` / `aq.avg` are device pointers or NULL.
+static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nframes, float *rows, long long row0,
+                           long long row_step, long long ring_rows, long long row_stride, long long store_from,
+                           float *peaks, bool accumulate, AvgReq aq) {
+    rfa_ctx *c = pl->ctx;
+    const int n = pl->d.fft_size;
+    SpectrumLaunch L{};
+    L.N = n;
+    L.in_fmt = pl->d.format;
+    L.out_kind = OUT_DB;
+    L.stream = c->stream;
+    L.num_sms = c->num_sms;
+    L.p.in = iq;
+    L.p.win = pl->win;
+    L.p.tw = pl->tw;
+    L.p.twN = pl->twN;
+    L.p.rows = rows;
+    L.p.row0 = row0;
+    L.p.row_step = row_step;
+    L.p.ring_rows = ring_rows;
+    L.p.row_stride = row_stride;
+    L.p.nframes = nframes;
+    L.p.store_from = store_from;
+    L.p.inv_n2 = 1.0f / ((float)n * (float)n);
+    L.p.peaks = peaks;
+    L.p.avg = aq.avg;
+    L.p.avg_newest = row0 + (nframes - 1) * row_step;
+    L.p.avg_dir = -row_step;
+    L.p.avg_valid = aq.valid;
+    L.p.avg_len = pl->d.avg_len;
+    L.p.ticket = pl->ticket.as<unsigned int>();
+    if (peaks && !accumulate) {  // FftProcessor.kt:236: "no peak" is -999999f
+        fill_f32(peaks, (size_t)n, -999999.0f, c->stream);
+        RFA_CK(cudaGetLastError());
+        c->launches++;
+    }
+    cudaError_t e = spectrum_launch(L);
+    if (e != cudaSuccess) return cuda_fail(e, "spectrum kernel");
+    c->launches++;
+    return RFA_OK;
+}
+
+extern "C" {
+
+int rfa_spectrum_plan_create(rfa_ctx *c, const rfa_spectrum_desc *d, rfa_spectrum_plan **out) {
+    RFA_REQUIRE(c && d && out, "rfa_spectrum_plan_create: NULL argument");
+    *out = nullptr;
+    RFA_REQUIRE(d->format >= RFA_FMT_S8 && d->format <= RFA_FMT_S16LE, "unknown sample format %d", d->format);
+    RFA_REQUIRE(is_pow2(d->fft_size) && d->fft_size >= 16 && d->fft_size <= 65536,
+                "FFT size %d unsupported: need a power of two in 16..65536", d->fft_size);
+    RFA_REQUIRE(d->window >= RFA_WIN_BLACKMAN_REF && d->window <= RFA_WIN_RECT, "unknown window %d", d->window);
+    RFA_REQUIRE(d->avg_len >= 0 && d->avg_len <= 30, "avg_len %d outside 0..30 (DisplayTab.kt:202-212)", d->avg_len);
+    if (int rc = c->use()) return rc;
+    rfa_spectrum_plan *pl = new rfa_spectrum_plan();
+    pl->ctx = c;
+    pl->d = *d;
+    const int n = d->fft_size, nl = n > 16384 ? 16384 : n;
+    int rc = c->get_twiddles(nl, &pl->tw);
+    if (!rc && n > 16384) rc = c->get_twiddles(-n, &pl->twN);
+    if (!rc) rc = c->get_window(d->window, n, &pl->win);
+    if (!rc) rc = pl->ticket.ensure(8 * sizeof(unsigned int));
+    if (!rc && cudaMemsetAsync(pl->ticket.p, 0, 8 * sizeof(unsigned int), c->stream) != cudaSuccess) rc = RFA_ERR_CUDA;
+    if (rc) {
+        delete pl;
+        return rc;
+    }
+    *out = pl;
+    return RFA_OK;
+}
+
+int rfa_spectrum_plan_destroy(rfa_spectrum_plan *pl) {
+    if (!pl) return RFA_OK;
+    cudaSetDevice(pl->ctx->device);
+    cudaStreamSynchronize(pl->ctx->stream);
+    pl->tail.release();
+    pl->ticket.release();
+    pl->dpeaks.release();
+    pl->davg.release();
+    for (int i = 0; i < 2; i++) {
+        pl->din[i].release();
+        pl->drows[i].release();
+    }
+    delete pl;
+    return RFA_OK;
+}
+
+long long rfa_spectrum_algorithmic_bytes(const rfa_spectrum_plan *pl, long long nframes, int rows_stored) {
+    if (!pl) return 0;
+    const long long n = pl->d.fft_size;
+    return nframes * n * (fmt_bytes(pl->d.format) + (rows_stored ? 4 : 0)) + 2 * n * 4;
+}
+
+int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframes, const rfa_spectrum_out *o,
+                         int mem) {
+    RFA_REQUIRE(pl && o, "rfa_spectrum_process: NULL argument");
+    RFA_REQUIRE(nframes >= 0, "negative frame count");
+    rfa_ctx *c = pl->ctx;
+    const int n = pl->d.fft_size, L = pl->d.avg_len;
+    const int bps = fmt_bytes(pl->d.format);
+    if (nframes == 0) return RFA_OK;
+    RFA_REQUIRE(iq != nullptr, "iq is NULL");
+    RFA_REQUIRE(!o->rows || o->row_stride >= n, "row_stride %lld smaller than the FFT size", o->row_stride);
+    RFA_REQUIRE(!o->rows || o->row_step == 1 || o->row_step == -1, "row_step must be +1 or -1");
+    RFA_REQUIRE(o->ring_rows >= 0, "negative ring_rows");
+    RFA_REQUIRE(!o->rows || o->ring_rows > 0 || o->row_step == 1, "a linear row buffer needs row_step == +1");
+    if (int rc = c->use()) return rc;
+    const bool want_peaks = o->peaks != nullptr && pl->d.peak_hold;
+    const bool want_avg = o->avg != nullptr;
+
+    if (mem == RFA_MEM_DEVICE) {
+        RFA_REQUIRE(((uintptr_t)iq % (bps == 4 ? 4 : 2)) == 0, "iq pointer misaligned for its format");
+        float *rows = o->rows;
+        long long row0 = o->row0, step = o->row_step, ring = o->ring_rows, stride = o->row_stride;
+        long long store_from = 0;
+        if (!rows) {
+            if (!want_avg && !want_peaks) return RFA_OK;  // nothing observable is requested
+            // keep just the newest L+1 rows for the time average
+            if (int rc = pl->tail.ensure((size_t)(L + 1) * n * sizeof(float))) return rc;
+            rows = pl->tail.as<float>();
+            row0 = 0;
+            step = 1;
+            ring = L + 1;
+            stride = n;
+            store_from = want_avg ? nframes - (L + 1) : nframes;
+        }
+        // more frames than ring rows: the older ones would be overwritten by newer frames of this
+        // very call (FftProcessor.kt:224-229 runs sequentially), so only the newest ring_rows
+        // frames are stored -- the frames are transformed concurrently, order must not matter
+        if (ring > 0 && nframes > ring && store_from < nframes - ring) store_from = nframes - ring;
+        AvgReq aq;
+        if (want_avg) {
+            aq.avg = o->avg;
+            aq.valid = nframes;
+            if (o->rows && o->ring_rows > 0) {
+                aq.valid = o->history_rows + nframes;
+                if (aq.valid > o->ring_rows) aq.valid = o->ring_rows;
+            }
+        }
+        return spectrum_device(pl, iq, nframes, rows, row0, step, ring, stride, store_from,
+                               want_peaks ? o->peaks : nullptr, o->peaks_accumulate != 0, aq);
+    }
+
+    // ---- host buffers: chunked H2D -> kernel -> D2H pipeline over three streams ----
+    RFA_REQUIRE(mem == RFA_MEM_HOST, "unknown memory space %d", mem);
+    RFA_REQUIRE(!o->rows || o->ring_rows == 0, "ring-buffer rows must be device resident");
+    const size_t frame_in = (size_t)n * bps, frame_out = (size_t)n * sizeof(float);
+    long long cf_frames = (long long)((8u << 20) / frame_in);  // ~8 MiB of IQ per chunk
+    if (cf_frames < L + 1) cf_frames = L + 1;
+    if (cf_frames > nframes) cf_frames = nframes;
+    const long long nchunks = nframes / cf_frames;  // the last chunk also takes the remainder
+    const long long max_chunk = cf_frames + nframes % cf_frames;
+    const bool store_rows = o->rows != nullptr;
+    for (int b = 0; b < 2; b++) {
+        if (int rc = pl->din[b].ensure(max_chunk * frame_in)) return rc;
+        if (store_rows || want_avg)
+            if (int rc = pl->drows[b].ensure(max_chunk * frame_out)) return rc;
+    }
+    float *dpeaks = nullptr;
+    if (want_peaks) {
+        if (int rc = pl->dpeaks.ensure(frame_out)) return rc;
+        dpeaks = pl->dpeaks.as<float>();
+        if (o->peaks_accumulate)
+            RFA_CK(cudaMemcpyAsync(dpeaks, o->peaks, frame_out, cudaMemcpyHostToDevice, c->stream));
+    }
+    // make the side streams start after whatever is already queued on the context stream
+    RFA_CK(cudaEventRecord(c->ev_k[0], c->stream));
+    RFA_CK(cudaEventRecord(c->ev_k[1], c->stream));
+    RFA_CK(cudaEventRecord(c->ev_out[0], c->stream));
+    RFA_CK(cudaEventRecord(c->ev_out[1], c->stream));
+    long long done = 0;
+    for (long long i = 0; i < nchunks; i++) {
+        const int b = (int)(i & 1);
+        const long long frames = (i == nchunks - 1) ? nframes - done : cf_frames;
+        RFA_CK(cudaStreamWaitEvent(c->s_in, c->ev_k[b], 0));  // kernel that last read din[b] is done
+        RFA_CK(cudaMemcpyAsync(pl->din[b].p, (const char *)iq + (size_t)done * frame_in, (size_t)frames * frame_in,
+                               cudaMemcpyHostToDevice, c->s_in));
+        RFA_CK(cudaEventRecord(c->ev_in[b], c->s_in));
+        RFA_CK(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+        RFA_CK(cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));  // drows[b] has been copied out
+        float *drows = (store_rows || want_avg) ? pl->drows[b].as<float>() : nullptr;
+        long long store_from = store_rows ? 0 : (want_avg && i == nchunks - 1 ? frames - (L + 1) : frames);
+        if (drows || dpeaks) {
+            float *rows_arg = drows ? drows : pl->din[b].as<float>();  // never written when store_from == frames
+            AvgReq aq;
+            if (want_avg && i == nchunks - 1) {
+                if (int rc = pl->davg.ensure(frame_out)) return rc;
+                aq.avg = pl->davg.as<float>();
+                aq.valid = nframes < frames ? nframes : frames;
+            }
+            if (int rc = spectrum_device(pl, pl->din[b].p, frames, rows_arg, 0, 1, 0, n, store_from, dpeaks,
+                                         o->peaks_accumulate != 0 || i > 0, aq))
+                return rc;
+        }
+        RFA_CK(cudaEventRecord(c->ev_k[b], c->stream));
+        if (store_rows) {
+            RFA_CK(cudaStreamWaitEvent(c->s_out, c->ev_k[b], 0));
+            if (o->row_stride == n) {
+                RFA_CK(cudaMemcpyAsync(o->rows + (size_t)(o->row0 + done) * n, drows, (size_t)frames * frame_out,
+                                       cudaMemcpyDeviceToHost, c->s_out));
+            } else {
+                RFA_CK(cudaMemcpy2DAsync(o->rows + (size_t)(o->row0 + done) * o->row_stride,
+                                         (size_t)o->row_stride * sizeof(float), drows, frame_out, frame_out,
+                                         (size_t)frames, cudaMemcpyDeviceToHost, c->s_out));
+            }
+            RFA_CK(cudaEventRecord(c->ev_out[b], c->s_out));
+        }
+        done += frames;
+    }
+    if (want_avg) RFA_CK(cudaMemcpyAsync(o->avg, pl->davg.p, frame_out, cudaMemcpyDeviceToHost, c->stream));
+    if (want_peaks) RFA_CK(cudaMemcpyAsync(o->peaks, dpeaks, frame_out, cudaMemcpyDeviceToHost, c->stream));
+    RFA_CK(cudaStreamSynchronize(c->s_out));
+    RFA_CK(cudaStreamSynchronize(c->stream));
+    return RFA_OK;
+}
+
+/* ---------------------------------------------------------------- row reductions ---- */
+int rfa_average_rows(rfa_ctx *c, const float *rows, long long newest, long long dir, long long ring_rows,
+                     long long row_stride, long long valid, int avg_len, int n, float *avg, int mem_rows,
+                     int mem_avg) {
+    RFA_REQUIRE(c && rows && avg, "rfa_average_rows: NULL argument");
+    RFA_REQUIRE(mem_rows == RFA_MEM_DEVICE, "rows must be device resident");
+    RFA_REQUIRE(avg_len >= 0 && avg_len <= 30 && n > 0, "bad averaging request");
+    if (int rc = c->use()) return rc;
+    float *davg = avg;
+    if (mem_avg == RFA_MEM_HOST) {
+        if (int rc = c->stage[4].ensure((size_t)n * sizeof(float))) return rc;
+        davg = c->stage[4].as<float>();
+    }
+    average_rows(rows, newest, dir, ring_rows, row_stride, valid, avg_len, n, davg, c->stream);
+    RFA_CK(cudaGetLastError());
+    c->launches++;
+    if (mem_avg == RFA_MEM_HOST) {
+        RFA_CK(cudaMemcpyAsync(avg, davg, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    }
+    return RFA_OK;
+}
+
+int rfa_channel_bins(int n, long long frequency, int sample_rate, long long chan_start, long long chan_end,
+                     int *bin_start, int *bin_end) {
+    RFA_REQUIRE(n > 0 && sample_rate > 0 && bin_start && bin_end, "rfa_channel_bins: bad argument");
+    design::channel_bins(n, frequency, sample_rate, chan_start, chan_end, bin_start, bin_end);
+    return RFA_OK;
+}
+
+int rfa_channel_strength(rfa_ctx *c, const float *rows, long long row0, long long row_step, long long ring_rows,
+                         long long row_stride, long long nrows, int bin_start, int bin_end, float *out,
+                         int mem_out) {
+    RFA_REQUIRE(c && rows && out, "rfa_channel_strength: NULL argument");
+    RFA_REQUIRE(bin_end > bin_start && bin_start >= 0, "empty channel bin range");
+    if (nrows <= 0) return RFA_OK;
+    if (int rc = c->use()) return rc;
+    float *dout = out;
+    if (mem_out == RFA_MEM_HOST) {
+        if (int rc = c->stage[4].ensure((size_t)nrows * sizeof(float))) return rc;
+        dout = c->stage[4].as<float>();
+    }
+    channel_strength(rows, row0, row_step, ring_rows, row_stride, nrows, bin_start, bin_end, dout, c->stream);
+    RFA_CK(cudaGetLastError());
+    c->launches++;
+    if (mem_out == RFA_MEM_HOST) {
+        RFA_CK(cudaMemcpyAsync(out, dout, (size_t)nrows * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    }
+    return RFA_OK;
+}
+
+int rfa_shift_rows(rfa_ctx *c, float *rows, long long nrows, long long row_stride, int n, int shift) {
+    RFA_REQUIRE(c && rows, "rfa_shift_rows: NULL argument");
+    RFA_REQUIRE(n > 0 && n <= 65536 && row_stride >= n, "bad row geometry");
+    if (int rc = c->use()) return rc;
+    shift_rows(rows, nrows, row_stride, n, shift, c->stream);
+    RFA_CK(cudaGetLastError());
+    c->launches++;
+    return RFA_OK;
+}
+
+int rfa_fill(rfa_ctx *c, float *dst, long long count, float value) {
+    RFA_REQUIRE(c && dst && count >= 0, "rfa_fill: bad argument");
+    if (int rc = c->use()) return rc;
+    fill_f32(dst, (size_t)count, value, c->stream);
+    RFA_CK(cudaGetLastError());
+    c->launches++;
+    return RFA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// rfa_fft_core.cuh -- register/shared-memory FFT building blocks for sm_100a.
+//
+// Replaces the reference's pffft (nativedsp/src/main/cpp/pffft.c:1173-1216 cfftf1_ps,
+// :291-425 passf*_ps, :1361-1403 pffft_cplx_finalize, :1324-1359 pffft_zreorder) with a
+// Stockham autosort transform: each thread owns 16 (or 32) complex points in registers,
+// radix-16/8/4/2 butterflies run entirely in registers and points are exchanged through a
+// padded shared-memory frame between passes.  Forward transform, unnormalised,
+// X[k] = sum x[n] exp(-2*pi*i*n*k/N), natural-order output -- the contract of
+// pffft_transform_ordered(..., PFFFT_FORWARD) (pffft.c:1904).
+//
+// Everything here is __host__ __device__ so tests/emu can run the exact index logic,
+// twiddle addressing and butterflies on the CPU (there is no GPU in the build box).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define RFA_HD __host__ __device__ __forceinline__
+#define RFA_CX __host__ __device__ constexpr
+#else
+#define RFA_HD inline
+#define RFA_CX constexpr
+#endif
+
+namespace rfa {
+
+struct cf {
+    float x, y;
+};
+
+RFA_HD cf cadd(cf a, cf b) { return cf{a.x + b.x, a.y + b.y}; }
+RFA_HD cf csub(cf a, cf b) { return cf{a.x - b.x, a.y - b.y}; }
+RFA_HD cf cmul(cf a, cf b) {
+    return cf{fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)};
+}
+RFA_HD cf mul_mj(cf a) { return cf{a.y, -a.x}; }  // a * (-j)
+
+RFA_CX int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
+
+// ---------------------------------------------------------------------------
+// In-register DFTs.  dftR(u) leaves natural-order output c in u[perm<R>(c)].
+// ---------------------------------------------------------------------------
+RFA_HD void bfly4(cf &a0, cf &a1, cf &a2, cf &a3) {
+    cf t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+template <int R>
+struct Dft;
+
+template <>
+struct Dft<2> {
+    static RFA_HD void run(cf *u) {
+        cf t = u[0];
+        u[0] = cadd(t, u[1]);
+        u[1] = csub(t, u[1]);
+    }
+    static RFA_CX int perm(int c) { return c; }
+};
+
+template <>
+struct Dft<4> {
+    static RFA_HD void run(cf *u) { bfly4(u[0], u[1], u[2], u[3]); }
+    static RFA_CX int perm(int c) { return c; }
+};
+
+template <>
+struct Dft<8> {
+    // even part in u[0,2,4,6], odd part in u[1,3,5,7]; X[k] -> u[2k], X[k+4] -> u[2k+1]
+    static RFA_HD void run(cf *u) {
+        const float h = 0.70710678118654752440f;
+        bfly4(u[0], u[2], u[4], u[6]);
+        bfly4(u[1], u[3], u[5], u[7]);
+        cf o1 = cf{h * (u[3].x + u[3].y), h * (u[3].y - u[3].x)};   // * W8^1
+        cf o2 = mul_mj(u[5]);                                       // * W8^2
+        cf o3 = cf{h * (u[7].y - u[7].x), -h * (u[7].x + u[7].y)};  // * W8^3
+        cf e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6], o0 = u[1];
+        u[0] = cadd(e0, o0);
+        u[1] = csub(e0, o0);
+        u[2] = cadd(e1, o1);
+        u[3] = csub(e1, o1);
+        u[4] = cadd(e2, o2);
+        u[5] = csub(e2, o2);
+        u[6] = cadd(e3, o3);
+        u[7] = csub(e3, o3);
+    }
+    static RFA_CX int perm(int c) { return 2 * (c & 3) + (c >> 2); }
+};
+
+template <>
+struct Dft<16> {
+    // 4x4 Cooley-Tukey: n = n2 + 4*n1, k = k1 + 4*k2.
+    // stage 1: DFT4 over n1 for each n2 -> u[n2 + 4*k1]; twiddle W16^(n2*k1);
+    // stage 2: DFT4 over n2 for each k1 -> X[k1 + 4*k2] in u[4*k1 + k2].
+    static RFA_HD void run(cf *u) {
+        const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+        const float h = 0.70710678118654752440f;
+#pragma unroll
+        for (int n2 = 0; n2 < 4; n2++) bfly4(u[n2], u[n2 + 4], u[n2 + 8], u[n2 + 12]);
+        // k1 = 1: W16^1, W16^2, W16^3
+        u[5] = cmul(u[5], cf{c1, -s1});
+        u[6] = cf{h * (u[6].x + u[6].y), h * (u[6].y - u[6].x)};
+        u[7] = cmul(u[7], cf{s1, -c1});
+        // k1 = 2: W16^2, W16^4, W16^6
+        u[9] = cf{h * (u[9].x + u[9].y), h * (u[9].y - u[9].x)};
+        u[10] = mul_mj(u[10]);
+        u[11] = cf{h * (u[11].y - u[11].x), -h * (u[11].x + u[11].y)};
+        // k1 = 3: W16^3, W16^6, W16^9
+        u[13] = cmul(u[13], cf{s1, -c1});
+        u[14] = cf{h * (u[14].y - u[14].x), -h * (u[14].x + u[14].y)};
+        u[15] = cmul(u[15], cf{-c1, s1});
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) bfly4(u[4 * k1], u[4 * k1 + 1], u[4 * k1 + 2], u[4 * k1 + 3]);
+    }
+    static RFA_CX int perm(int c) { return 4 * (c & 3) + (c >> 2); }
+};
+
+// ---------------------------------------------------------------------------
+// Frame geometry.  NL = points transformed inside one CTA slot (shared memory),
+// T = threads cooperating on the frame, E = NL/T points per thread.
+// Radix plan: as many radix-16 passes as fit, then one radix-2/4/8 pass.
+// ---------------------------------------------------------------------------
+template <int NL>
+struct Plan {
+    static constexpr int LG = ilog2c(NL);
+    static constexpr int N16 = LG / 4;
+    static constexpr int REM = LG % 4;
+    static constexpr int PASSES = N16 + (REM ? 1 : 0);
+    static RFA_CX int radix(int pass) { return pass < N16 ? 16 : (1 << REM); }
+    // product of the radices of all passes before `pass`
+    static RFA_CX int prod(int pass) { return pass == 0 ? 1 : prod(pass - 1) * radix(pass - 1); }
+    // padded shared-memory frame: one pad slot per 16 points keeps the radix-R
+    // scatter of the first pass (stride R) and the stride-1 gathers conflict free
+    static constexpr int SMEM_POINTS = NL + NL / 16;
+};
+
+RFA_HD int phys(int a) { return a + (a >> 4); }
+
+// Twiddle tables are stored per pass so that a warp's loads are contiguous: pass with
+// radix R and stride product P keeps W_{P*R}^{k*r} at  pass_tw_offset + (r-1)*P + k
+// (k = 0..P-1 is the fast index = consecutive lanes).  Total size < NL entries.
+template <int NL>
+RFA_CX int pass_tw_offset(int pass) {
+    return pass <= 1 ? 0 : pass_tw_offset<NL>(pass - 1) + (Plan<NL>::radix(pass - 1) - 1) * Plan<NL>::prod(pass - 1);
+}
+template <int NL>
+RFA_CX int pass_tw_total() {
+    return pass_tw_offset<NL>(Plan<NL>::PASSES);
+}
+
+// One pass, gather side: butterfly i takes x[i + r*NL/R], r < R, applies the Stockham
+// twiddle W_{P*R}^{k*r} (k = i mod P), runs the DFT.  `tw` points at this pass's table.
+// `u` holds E/R butterflies of R points each, butterfly b is i = tid + b*T.
+// All strides are multiples of 16, so phys(i + r*STR) = phys(i) + r*(STR + STR/16): one
+// address per butterfly, the rest are immediate offsets.
+template <int NL, int T, int R, int P>
+RFA_HD void pass_gather(const cf *x, const cf *tw, int tid, cf *u) {
+    constexpr int E = NL / T;
+    constexpr int NB = E / R;
+    constexpr int STR = NL / R;
+    static_assert(STR % 16 == 0 || NL < 256, "stride must keep the padding pattern");
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int i = tid + b * T;
+        const int k = i & (P - 1);
+        const cf *twk = tw + k;
+        if (STR % 16 == 0) {
+            const cf *xi = x + phys(i);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                cf v = xi[r * (STR + STR / 16)];
+                if (P > 1 && r > 0) v = cmul(v, twk[(r - 1) * P]);
+                u[b * R + r] = v;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                cf v = x[phys(i + r * STR)];
+                if (P > 1 && r > 0) v = cmul(v, twk[(r - 1) * P]);
+                u[b * R + r] = v;
+            }
+        }
+        Dft<R>::run(u + b * R);
+    }
+}
+
+// One pass, scatter side: natural-order output c of butterfly i goes to
+// y[(i-k)*R + k + c*P].  For P a multiple of 16 the c-offsets are immediates; the first
+// pass (P = 1, R = 16) writes 16 consecutive points, phys(16*i + c) = 17*i + c.
+template <int NL, int T, int R, int P>
+RFA_HD void pass_scatter(cf *y, int tid, const cf *u) {
+    constexpr int E = NL / T;
+    constexpr int NB = E / R;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int i = tid + b * T;
+        const int k = i & (P - 1);
+        const int j = (i - k) * R + k;
+        if (P % 16 == 0) {
+            cf *yj = y + phys(j);
+#pragma unroll
+            for (int c = 0; c < R; c++) yj[c * (P + P / 16)] = u[b * R + Dft<R>::perm(c)];
+        } else if (P == 1 && R == 16) {
+            cf *yj = y + 17 * i;
+#pragma unroll
+            for (int c = 0; c < R; c++) yj[c] = u[b * R + Dft<R>::perm(c)];
+        } else {
+#pragma unroll
+            for (int c = 0; c < R; c++) y[phys(j + c * P)] = u[b * R + Dft<R>::perm(c)];
+        }
+    }
+}
+
+// First pass without the gather: caller filled u[b*R + r] with point (tid + b*T) + r*NL/R.
+template <int NL, int T, int R>
+RFA_HD void pass_first_compute(cf *u) {
+    constexpr int NB = (NL / T) / R;
+#pragma unroll
+    for (int b = 0; b < NB; b++) Dft<R>::run(u + b * R);
+}
+
+// Output bin of natural-order output c of butterfly b in the LAST pass (P*R == NL):
+// (i-k)*R + k + c*P with k = i  ->  i + c*P.
+template <int NL, int T, int R, int P>
+RFA_HD int last_pass_bin(int tid, int b, int c) {
+    return (tid + b * T) + c * P;
+}
+
+// ---------------------------------------------------------------------------
+// Sample conversion, bit-exact with the reference's look-up tables.
+//   s8 : Signed8BitIQConverter.java:48-50     lut[i] = (i-128)/128.0f, index b+128
+//   u8 : Unsigned8BitIQConverter.java:48-50   lut[i] = (i-127.4f)/128.0f
+//   s16: Signed16BitIQConverter.kt:46-57      lut[u] = s/32768.0f
+// Every value is an integer (or integer minus 127.4f, a multiple of 2^-17 below 128)
+// scaled by a power of two, so the arithmetic forms below round nowhere and equal
+// the tables for all code points (checked exhaustively in tests).
+// ---------------------------------------------------------------------------
+enum : int { FMT_S8 = 0, FMT_U8 = 1, FMT_S16LE = 2, FMT_CF32 = 3, FMT_PF32 = 4 };
+
+RFA_HD float conv_s8(int b /* -128..127 */) { return (float)b * 0.0078125f; }
+RFA_HD float conv_u8(int b /* 0..255 */) { return ((float)b - 127.4f) * 0.0078125f; }
+RFA_HD float conv_s16(int s /* -32768..32767 */) { return (float)s * (1.0f / 32768.0f); }
+
+// The same conversions without an int->float instruction (I2F shares the quarter-rate
+// XU pipe with the log2 of the dB stage): the code is dropped into the mantissa of 2^23,
+// so  bits(0x4B000000 | u) == 8388608.0f + u  exactly, and one FADD recovers the integer.
+// `ws` is the window tap times the power-of-two unit (1/128 or 1/32768): scaling by a power
+// of two commutes with rounding, so value*ws == fl(lut[code] * w), the reference's product.
+RFA_HD float bits_to_float(uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+// PRMT: result byte i = byte (sel >> 4i) & 7 of the pair {a = bytes 0-3, b = bytes 4-7}
+RFA_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t ab = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((ab >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+#endif
+}
+// one PRMT drops byte 0 / byte 1 (or half 0 / half 1) of `raw` into the mantissa of 2^23
+RFA_HD float magic_byte0(uint32_t raw) { return bits_to_float(byte_perm(raw, 0x4B000000u, 0x7650u)); }
+RFA_HD float magic_byte1(uint32_t raw) { return bits_to_float(byte_perm(raw, 0x4B000000u, 0x7651u)); }
+RFA_HD float magic_half0(uint32_t raw) { return bits_to_float(byte_perm(raw, 0x4B000000u, 0x7610u)); }
+RFA_HD float magic_half1(uint32_t raw) { return bits_to_float(byte_perm(raw, 0x4B000000u, 0x7632u)); }
+
+// dB scaling of nativedsp.cpp:72-79: 10*log10(sqrt((re/N)^2+(im/N)^2)) = 5*log10(|X|^2/N^2)
+RFA_HD float logmag_db(cf v, float inv_n2) {
+    float pw = fmaf(v.x, v.x, v.y * v.y) * inv_n2;
+#ifdef __CUDA_ARCH__
+    float lg;  // MUFU.LG2 without the denormal pre-scaling: |X|^2/N^2 is far from 1e-38, 0 -> -inf
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(pw));
+    return 1.5051499783199060f * lg;
+#else
+    return 1.5051499783199060f * log2f(pw);
+#endif
+}
+
+}  // namespace rfa

@@ -1,0 +1,490 @@
+// spectrum_kernel.cuh -- the fused IQ -> spectrum kernel (K3 of SURVEY.md 2b).
+//
+// One launch does, per FFT frame, what the reference spreads over three threads:
+//   Scheduler.kt:266          fillPacketIntoSamplePacket   bytes -> float re/im   (LUT)
+//   NativeDsp.kt:55-58        re*w, im*w                   Blackman window
+//   nativedsp.cpp:69          pffft_transform_ordered      forward C2C FFT
+//   nativedsp.cpp:72-79       10*log10(sqrt((re/N)^2+(im/N)^2)) at (i+N/2)%N
+//   FftProcessor.kt:224       waterfall row store
+//   FftProcessor.kt:244       peaks = max(peaks, row)
+// so an IQ sample crosses HBM once (2 or 4 bytes in) and one float per bin goes out.
+//
+// Layout: a CTA slot of T threads owns one frame of NL points in a padded shared
+// frame; each thread keeps E = NL/T points in registers.  CTAs are persistent: the grid
+// is sized to the machine and every slot walks frames slot, slot+G, slot+2G, ...  The
+// bins a thread produces in the last pass do not depend on the frame, so the peak-hold
+// running maximum lives in registers for the whole launch and is written once.
+//
+// N > 16384 does not fit one SM's shared memory.  It is split N = S * NL (S = 2, 4):
+// CTA residue c computes bins k = c + S*k2 by folding the S strided input sections with
+// W_S^(n1*c), rotating by W_N^(n2*c) and running the NL-point transform -- the raw input
+// (2-4 B/sample) is re-read S times from L2, nothing is exchanged between CTAs.
+#pragma once
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#endif
+
+#include "rfa_fft_core.cuh"
+
+namespace rfa {
+
+enum : int { OUT_DB = 0, OUT_CPLX = 1 };
+
+struct SpectrumParams {
+    const void *in;       // raw IQ (s8/u8 pairs, s16le pairs, interleaved cf32) or planar re
+    const float *in_im;   // planar im (FMT_PF32 only)
+    const float *win;     // [N] window, nullptr = rectangular
+    const cf *tw;         // per-pass Stockham twiddles (make_pass_twiddles(NL))
+    const cf *twN;        // [N]  exp(-2*pi*i*t/N), only read when S > 1
+    float *rows;          // OUT_DB: dB rows; OUT_CPLX: interleaved complex spectra
+    long long row0;       // output row of frame f = (row0 + f*row_step) mod ring_rows
+    long long row_step;
+    long long ring_rows;  // 0 = no wrap
+    long long row_stride; // floats between rows
+    long long nframes;
+    long long store_from; // rows of frames < store_from are not written (peak-only runs)
+    float *peaks;         // [N] running maxima, merged with float atomics at kernel end, or nullptr
+    float *avg;           // [N] mean of the newest avg_len+1 rows (computed by the tail CTA group), or nullptr
+    long long avg_newest; // row index of the newest row after this launch
+    long long avg_dir;    // step towards older rows (-row_step)
+    long long avg_valid;  // rows that hold data; older terms count as -9999f
+    int avg_len;          // L
+    unsigned int *ticket; // [8] zeroed counters: [c] finished tail rows, [4+c] CTAs done averaging (residue c < 4)
+    float inv_n2;         // 1/N^2
+};
+
+template <int NL>
+struct Geom {
+    static constexpr int T = NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1));
+    static constexpr int E = NL / T;
+    static constexpr int FPC = T >= 256 ? 1 : 256 / T;   // frames per CTA
+    static constexpr int CTA = T * FPC;
+    // two ping-pong frames per slot (one barrier per pass) while they fit comfortably
+    static constexpr int NBUF = NL <= 8192 ? 2 : 1;
+    static constexpr size_t SMEM = (size_t)FPC * NBUF * Plan<NL>::SMEM_POINTS * sizeof(cf);
+};
+
+RFA_HD cf rot_q(cf v, int q) {  // v * (-j)^q
+    q &= 3;
+    if (q == 1) return cf{v.y, -v.x};
+    if (q == 2) return cf{-v.x, -v.y};
+    if (q == 3) return cf{-v.y, v.x};
+    return v;
+}
+
+// one input point (index n inside frame f of N points), converted and multiplied by
+// ws = window tap * unit scale of the format (see unit_scale)
+template <int IN>
+RFA_CX float unit_scale() {
+    return IN == FMT_S16LE ? (1.0f / 32768.0f) : ((IN == FMT_S8 || IN == FMT_U8) ? 0.0078125f : 1.0f);
+}
+
+// integer code pair in a register -> (I, Q) * ws
+template <int IN>
+RFA_HD cf decode_point(uint32_t raw, float ws) {
+    cf v;
+    if (IN == FMT_S8) {
+        raw ^= 0x8080u;  // two's complement -> offset binary: code + 128
+        v.x = (magic_byte0(raw) - 8388736.0f) * ws;
+        v.y = (magic_byte1(raw) - 8388736.0f) * ws;
+    } else if (IN == FMT_U8) {
+        v.x = ((magic_byte0(raw) - 8388608.0f) - 127.4f) * ws;
+        v.y = ((magic_byte1(raw) - 8388608.0f) - 127.4f) * ws;
+    } else {
+        raw ^= 0x80008000u;
+        v.x = (magic_half0(raw) - 8421376.0f) * ws;
+        v.y = (magic_half1(raw) - 8421376.0f) * ws;
+    }
+    return v;
+}
+
+template <int IN>
+RFA_HD cf load_point(const void *in, const float *in_im, long long idx, float ws) {
+    cf v;
+    if (IN == FMT_S8 || IN == FMT_U8) {
+        v = decode_point<IN>((uint32_t)((const uint16_t *)in)[idx], ws);
+    } else if (IN == FMT_S16LE) {
+        v = decode_point<IN>(((const uint32_t *)in)[idx], ws);
+    } else if (IN == FMT_CF32) {
+        v = ((const cf *)in)[idx];
+        v.x *= ws;
+        v.y *= ws;
+    } else {
+        v.x = ((const float *)in)[idx] * ws;
+        v.y = in_im[idx] * ws;
+    }
+    return v;
+}
+
+template <int IN>
+RFA_CX int in_elem_bytes() {
+    return IN == FMT_S16LE ? 4 : (IN == FMT_CF32 ? 8 : (IN == FMT_PF32 ? 4 : 2));
+}
+
+// Everything one thread does for one frame between two barriers is a "phase"; the
+// kernel and the CPU emulation (tests/emu) call the same phase functions.
+template <int NL, int S, int IN, int OUT>
+struct SpectrumFrame {
+    using G = Geom<NL>;
+    using PL = Plan<NL>;
+    static constexpr int T = G::T, E = G::E, N = NL * S;
+    static constexpr int LAST = PL::PASSES - 1;
+    // raw codes of the next frame are fetched while the current one is transformed
+    static constexpr bool PREFETCH = (S == 1) && (E <= 16) && (IN == FMT_S8 || IN == FMT_U8 || IN == FMT_S16LE);
+    // twiddles of the last pass live in registers when there are few enough of them
+    static constexpr int LAST_TW = PL::PASSES > 1 ? (E / PL::radix(LAST)) * (PL::radix(LAST) - 1) : 0;
+    static constexpr bool LAST_TW_REG = LAST_TW > 0 && LAST_TW <= 16;
+    // twiddle tables of the middle passes are staged in shared memory (<= 32 KB)
+    static constexpr int MID_TW = PL::PASSES > 2 ? pass_tw_offset<NL>(LAST) : 0;
+    static constexpr bool MID_TW_SMEM = MID_TW > 0 && MID_TW <= 4096;
+    static constexpr size_t SMEM_BYTES = G::SMEM + (MID_TW_SMEM ? MID_TW * sizeof(cf) : 0);
+
+    // phase 0a: fetch the raw codes of frame f (integer formats)
+    // `src` points at point `tid` of the frame
+    static RFA_HD void load_raw(const char *src, uint32_t *raw) {
+        constexpr int R = PL::radix(0);
+        constexpr int NB = E / R, STR = NL / R;
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int off = b * T + r * STR;
+                raw[b * R + r] = (IN == FMT_S16LE) ? ((const uint32_t *)src)[off] : (uint32_t)((const uint16_t *)src)[off];
+            }
+    }
+    // phase 0b: convert + window, first radix pass in registers
+    static RFA_HD void first_from_raw(const uint32_t *raw, const float *wreg, cf *u) {
+        constexpr int R = PL::radix(0);
+#pragma unroll
+        for (int e = 0; e < E; e++) u[e] = decode_point<IN>(raw[e], wreg[e]);
+        pass_first_compute<NL, T, R>(u);
+    }
+
+    // phase 0 (non-prefetching formats and split transforms): gather + convert + window + fold
+    static RFA_HD void first(const SpectrumParams &p, long long f, int c, int tid, const float *wreg, cf *u) {
+        constexpr int R = PL::radix(0);
+        constexpr int NB = E / R, STR = NL / R;
+        // one 64-bit address per frame; every point of this thread is a constant offset from it
+        const char *src = (const char *)p.in + (f * (long long)N + tid) * in_elem_bytes<IN>();
+        const float *src_im = (IN == FMT_PF32) ? p.in_im + (f * (long long)N + tid) : nullptr;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int off = b * T + r * STR;
+                cf acc;
+                if (S == 1) {
+                    acc = load_point<IN>(src, src_im, off, wreg[b * R + r]);
+                } else {
+                    const int n2 = tid + off;
+                    acc = cf{0.f, 0.f};
+#pragma unroll
+                    for (int n1 = 0; n1 < S; n1++) {
+                        const float ws = p.win ? p.win[n2 + n1 * NL] * unit_scale<IN>() : unit_scale<IN>();
+                        const cf v = load_point<IN>(src, src_im, off + n1 * NL, ws);
+                        acc = cadd(acc, rot_q(v, n1 * c * (4 / S)));
+                    }
+                    if (c != 0) acc = cmul(acc, p.twN[(n2 * c) & (N - 1)]);
+                }
+                u[b * R + r] = acc;
+            }
+        }
+        pass_first_compute<NL, T, R>(u);
+    }
+
+    template <int PASS>
+    static RFA_HD void scatter(cf *x, int tid, const cf *u) {
+        pass_scatter<NL, T, PL::radix(PASS), PL::prod(PASS)>(x, tid, u);
+    }
+    // `tw` is the base of the per-pass tables (global or the shared-memory copy)
+    template <int PASS>
+    static RFA_HD void gather(const cf *x, const cf *tw, int tid, cf *u) {
+        pass_gather<NL, T, PL::radix(PASS), PL::prod(PASS)>(x, tw + pass_tw_offset<NL>(PASS), tid, u);
+    }
+    // last pass with its twiddles held by the thread: twreg[b*(R-1) + r-1]
+    static RFA_HD void load_last_tw(const cf *tw, int tid, cf *twreg) {
+        constexpr int R = PL::radix(LAST), P = PL::prod(LAST), NB = E / R;
+        const cf *t = tw + pass_tw_offset<NL>(LAST);
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int r = 1; r < R; r++) twreg[b * (R - 1) + r - 1] = t[(r - 1) * P + ((tid + b * T) & (P - 1))];
+    }
+    static RFA_HD void gather_last_reg(const cf *x, const cf *twreg, int tid, cf *u) {
+        constexpr int R = PL::radix(LAST), NB = E / R, STR = NL / R;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const cf *xi = x + phys(tid + b * T);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                cf v = xi[r * (STR + STR / 16)];
+                if (r > 0) v = cmul(v, twreg[b * (R - 1) + r - 1]);
+                u[b * R + r] = v;
+            }
+            Dft<R>::run(u + b * R);
+        }
+    }
+
+    // final phase: dB (or raw complex) to the output row, running peak maximum.
+    // `out` is the row base (row index resolved by the caller).  Bin k = c + S*(tid + b*T + cc*P)
+    // and tid + b*T < P <= N/2/S, so the fft-shift XOR only touches the constant part.
+    template <bool PEAK, bool STORE>
+    static RFA_HD void emit(float *out, int c, int tid, const cf *u, float *pk, float inv_n2) {
+        constexpr int R = PL::radix(LAST), P = PL::prod(LAST), NB = E / R;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            if (OUT == OUT_CPLX) {
+                cf *o = (cf *)out + (c + S * (tid + b * T));
+#pragma unroll
+                for (int cc = 0; cc < R; cc++)
+                    if (STORE) o[S * cc * P] = u[b * R + Dft<R>::perm(cc)];
+            } else {
+                float *o = out + (c + S * (tid + b * T));
+#pragma unroll
+                for (int cc = 0; cc < R; cc++) {
+                    const float db = logmag_db(u[b * R + Dft<R>::perm(cc)], inv_n2);
+                    if (STORE) o[shifted_offset(S * cc * P)] = db;
+                    if (PEAK) pk[b * R + cc] = fmaxf(pk[b * R + cc], db);
+                }
+            }
+        }
+    }
+    // offset of bin (base + d) after the fft-shift, relative to base, for d a multiple of
+    // S*P with base < S*P: (base + d) ^ (N/2) = base + (d ^ (N/2)) when N/2 is a multiple of S*P
+    static RFA_CX int shifted_offset(int d) {
+        return (PL::prod(PL::PASSES - 1) * S <= N / 2) ? (d ^ (N >> 1)) : d;
+    }
+    // shifted output index of peak register e (= b*R + cc) of thread tid
+    static RFA_HD int peak_index(int c, int tid, int e) {
+        constexpr int R = PL::radix(LAST), P = PL::prod(LAST);
+        const int b = e / R, cc = e % R;
+        return (c + S * (tid + b * T + cc * P)) ^ (N >> 1);
+    }
+};
+
+// row of frame f: (row0 + f*row_step) mod ring_rows
+RFA_HD long long frame_row(const SpectrumParams &p, long long f) {
+    long long row = p.row0 + f * p.row_step;
+    if (p.ring_rows > 0) {
+        row %= p.ring_rows;
+        if (row < 0) row += p.ring_rows;
+    }
+    return row;
+}
+
+// AnalyzerSurface.kt:683-684,710-714 for bin i: newest -> oldest, float32, divided by L+1
+template <class LoadFn>
+RFA_HD float boxcar_average(const SpectrumParams &p, int i, LoadFn load) {
+    float sum = 0.0f;
+    for (int r = 0; r <= p.avg_len; r++) {
+        float v = -9999.0f;
+        if (r < p.avg_valid) {
+            long long row = p.avg_newest + (long long)r * p.avg_dir;
+            if (p.ring_rows > 0) {
+                row %= p.ring_rows;
+                if (row < 0) row += p.ring_rows;
+            }
+            v = load(p.rows + row * p.row_stride + i);
+        }
+        sum = sum + v;
+    }
+    return sum / (float)(p.avg_len + 1);
+}
+
+#ifdef __CUDACC__
+// max for floats of either sign through the integer atomics (RED.MAX / RED.MIN)
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+    if (v >= 0.0f)
+        atomicMax((int *)addr, __float_as_int(v));
+    else
+        atomicMin((unsigned int *)addr, __float_as_uint(v));
+}
+
+// Passes 1 .. PASSES-1 of one frame.  With two shared frames (NBUF == 2) pass k scatters into
+// buffer (k-1)&1 and gathers from it after ONE barrier: the buffer being overwritten was last
+// read two barriers ago.  With a single frame a second barrier protects the gather.
+template <int NL, int S, int IN, int OUT, int PASS>
+struct MiddlePasses {
+    // tw_mid: tables of the middle passes (shared-memory copy when it fits), tw_all: the
+    // complete global table (the last pass reads it when its twiddles are not in registers)
+    static __device__ __forceinline__ void run(cf *x0, cf *x1, const cf *tw_mid, const cf *tw_all, const cf *twreg,
+                                               int tid, cf *u) {
+        using F = SpectrumFrame<NL, S, IN, OUT>;
+        if constexpr (PASS < Plan<NL>::PASSES) {
+            cf *x = ((PASS - 1) & 1) ? x1 : x0;
+            F::template scatter<PASS - 1>(x, tid, u);
+            __syncthreads();
+            if constexpr (PASS == F::LAST && F::LAST_TW_REG)
+                F::gather_last_reg(x, twreg, tid, u);
+            else if constexpr (PASS == F::LAST)
+                F::template gather<PASS>(x, tw_all, tid, u);
+            else
+                F::template gather<PASS>(x, tw_mid, tid, u);
+            if constexpr (Geom<NL>::NBUF == 1 && PASS + 1 < Plan<NL>::PASSES) __syncthreads();
+            MiddlePasses<NL, S, IN, OUT, PASS + 1>::run(x0, x1, tw_mid, tw_all, twreg, tid, u);
+        }
+    }
+};
+
+// Frame schedule.  Work item v (0 .. nframes-1) is frame nframes-1-v: the newest frames are
+// transformed FIRST, by the first groups in their first iteration.  Item v belongs to slot
+// (v mod slots) and is that slot's iteration (v div slots), slots = groups * FPC.
+// The newest avg_len+1 frames ("tail") are therefore finished a few microseconds into the
+// launch; every CTA averages a slice of the bins once it has run out of frames.
+// All per-frame addresses advance by constants, so the loop carries two pointers and a counter.
+template <int NL, int S, int IN, int OUT>
+__global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? 2 : 1) spectrum_kernel(const SpectrumParams p) {
+    using G = Geom<NL>;
+    using F = SpectrumFrame<NL, S, IN, OUT>;
+    constexpr int T = G::T, E = G::E, FPC = G::FPC, N = NL * S;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int sub = threadIdx.x / T, tid = threadIdx.x % T;
+    cf *x0 = reinterpret_cast<cf *>(smem_raw) + (size_t)sub * G::NBUF * Plan<NL>::SMEM_POINTS;
+    cf *x1 = G::NBUF == 2 ? x0 + Plan<NL>::SMEM_POINTS : x0;
+
+    const int c = (S == 1) ? 0 : (int)(blockIdx.x % S);
+    const int groups = gridDim.x / S, group = blockIdx.x / S;
+    const long long slots = (long long)groups * FPC, slot = (long long)group * FPC + sub;
+    // iteration counts (frames per slot fit an int: a slot never sees more than 2^31 frames)
+    const int iters = (int)((p.nframes + slots - 1) / slots);                 // CTA-uniform
+    const int my_iters = slot < p.nframes ? (int)((p.nframes - slot + slots - 1) / slots) : 0;
+    const bool want_avg = (OUT == OUT_DB) && p.avg != nullptr;
+    const bool want_peak = (OUT == OUT_DB) && p.peaks != nullptr;
+    const long long n_tail = want_avg ? (p.nframes < p.avg_len + 1 ? p.nframes : p.avg_len + 1) : 0;
+    // rows of frames >= store_from are written: items v <= nframes-1-store_from
+    int store_iters = my_iters;
+    if (p.store_from > 0) {
+        const long long vmax = p.nframes - 1 - p.store_from;  // may be negative
+        store_iters = vmax >= slot ? (int)((vmax - slot) / slots) + 1 : 0;
+    }
+    // iterations in which this CTA finishes tail rows (items group*FPC + it*slots < n_tail)
+    const int tail_iters = (want_avg && (long long)group * FPC < n_tail)
+                               ? (int)((n_tail - (long long)group * FPC + slots - 1) / slots)
+                               : 0;
+
+    // middle-pass twiddle tables: one shared-memory copy per CTA
+    const cf *tw = p.tw;
+    if constexpr (F::MID_TW_SMEM) {
+        cf *stw = reinterpret_cast<cf *>(smem_raw + G::SMEM);
+        for (int i = threadIdx.x; i < F::MID_TW; i += G::CTA) stw[i] = p.tw[i];
+        tw = stw;
+        __syncthreads();
+    }
+    // last-pass twiddles and window taps of this thread never change: registers.
+    // The window is pre-multiplied by the format's power-of-two unit.
+    cf twreg[F::LAST_TW_REG ? F::LAST_TW : 1];
+    if constexpr (F::LAST_TW_REG) F::load_last_tw(p.tw, tid, twreg);
+    float wreg[E];
+    if (S == 1) {
+        constexpr int R = Plan<NL>::radix(0), STR = NL / R;
+#pragma unroll
+        for (int b = 0; b < E / R; b++)
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                wreg[b * R + r] = (p.win ? p.win[tid + b * T + r * STR] : 1.0f) * unit_scale<IN>();
+    }
+    float pk[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) pk[e] = -999999.0f;
+
+    // frame of iteration `it` is f = nframes-1-slot - it*slots: input and (linear) row pointers
+    // step by constants
+    long long f = p.nframes - 1 - slot;
+    const char *src = (const char *)p.in + (f * (long long)N + tid) * in_elem_bytes<IN>();
+    const long long src_step = slots * (long long)N * in_elem_bytes<IN>();
+    float *out = p.rows + (p.ring_rows > 0 ? 0 : (p.row0 + f * p.row_step) * p.row_stride);
+    const long long out_step = slots * p.row_step * p.row_stride;
+    const float inv_n2 = p.inv_n2;
+
+    cf u[E];
+    uint32_t raw[F::PREFETCH ? E : 1];
+    if constexpr (F::PREFETCH)
+        if (my_iters > 0) F::load_raw(src, raw);
+
+    for (int it = 0; it < iters; it++) {
+        const bool active = it < my_iters;
+        if constexpr (F::PREFETCH) {
+            if (active) F::first_from_raw(raw, wreg, u);
+            src -= src_step;
+            if (it + 1 < my_iters) F::load_raw(src, raw);  // lands while this frame is transformed
+        } else {
+            if (active) F::first(p, f, c, tid, wreg, u);
+        }
+        // single frame buffer: the previous frame's last gather must be done before the first
+        // scatter; with ping-pong buffers and an even number of exchanges the barriers inside
+        // the passes already order it (PASSES-1 exchanges alternate A,B,A,...)
+        if (it > 0 && (G::NBUF == 1 || ((Plan<NL>::PASSES - 1) & 1))) __syncthreads();
+        if constexpr (Plan<NL>::PASSES > 1) MiddlePasses<NL, S, IN, OUT, 1>::run(x0, x1, tw, p.tw, twreg, tid, u);
+        if (active) {
+            if (p.ring_rows > 0) out = p.rows + frame_row(p, f) * p.row_stride;
+            if (it < store_iters) {
+                if (want_peak)
+                    F::template emit<true, true>(out, c, tid, u, pk, inv_n2);
+                else
+                    F::template emit<false, true>(out, c, tid, u, pk, inv_n2);
+            } else if (want_peak) {
+                F::template emit<true, false>(out, c, tid, u, pk, inv_n2);
+            }
+        }
+        f -= slots;
+        out -= out_step;
+        // publish finished tail rows (CTA-uniform test; only the first iteration or two)
+        if (it < tail_iters) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const long long v0 = (long long)group * FPC + it * slots;
+                const long long cnt = (n_tail - v0 < FPC) ? n_tail - v0 : FPC;
+                atomicAdd(p.ticket + c, (unsigned int)cnt);
+            }
+        }
+    }
+
+    if (want_peak && my_iters > 0) {
+#pragma unroll
+        for (int e = 0; e < E; e++) atomic_max_float(p.peaks + F::peak_index(c, tid, e), pk[e]);
+    }
+
+    // time average (AnalyzerSurface.kt:710-714).  The tail rows were finished long ago by CTAs
+    // that wait on nobody; every CTA takes a slice of its residue's bins, one bin per thread,
+    // all L+1 loads of a bin in flight at once, summed newest -> oldest in float32.
+    if (want_avg) {
+        if (threadIdx.x == 0) {
+            volatile unsigned int *t = p.ticket + c;
+            while (*t < (unsigned int)n_tail) __nanosleep(64);
+        }
+        __syncthreads();
+        __threadfence();
+        for (int i = c + S * (group + groups * (int)threadIdx.x); i < N; i += S * groups * G::CTA) {
+            float v[31];
+#pragma unroll
+            for (int r = 0; r < 31; r++) {
+                v[r] = -9999.0f;
+                if (r <= p.avg_len && r < p.avg_valid) {
+                    long long row = p.avg_newest + (long long)r * p.avg_dir;
+                    if (p.ring_rows > 0) {
+                        row %= p.ring_rows;
+                        if (row < 0) row += p.ring_rows;
+                    }
+                    v[r] = __ldcg(p.rows + row * p.row_stride + i);
+                }
+            }
+            float sum = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 31; r++)
+                if (r <= p.avg_len) sum = __fadd_rn(sum, v[r]);
+            p.avg[i] = __fdiv_rn(sum, (float)(p.avg_len + 1));
+        }
+        // the last CTA of this residue to get here re-arms the counters for the next launch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(p.ticket + 4 + c, 1u) == (unsigned int)groups - 1u) {
+                p.ticket[c] = 0u;
+                p.ticket[4 + c] = 0u;
+            }
+        }
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace rfa

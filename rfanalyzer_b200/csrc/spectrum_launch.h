@@ -1,0 +1,43 @@
+// spectrum_launch.h -- host-side interface of the fused spectrum kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "spectrum_kernel.cuh"
+
+namespace rfa {
+
+struct SpectrumLaunch {
+    int N;         // FFT size, power of two, 16 .. 65536
+    int in_fmt;    // FMT_*
+    int out_kind;  // OUT_DB / OUT_CPLX
+    SpectrumParams p;
+    cudaStream_t stream;
+    int num_sms;
+    int max_grid;  // 0 = size to the machine
+};
+
+// number of CTAs the launcher will use and the per-CTA frame slots (for peak_partial sizing)
+cudaError_t spectrum_grid(int N, int in_fmt, int out_kind, long long nframes, int num_sms, int max_grid,
+                          int *grid, int *slots_per_cta);
+cudaError_t spectrum_launch(const SpectrumLaunch &L);
+
+// instantiation groups (one translation unit each, see spectrum_inst.cu)
+cudaError_t spectrum_group0(const SpectrumLaunch &L, bool query, int *grid, int *spc);
+cudaError_t spectrum_group1(const SpectrumLaunch &L, bool query, int *grid, int *spc);
+cudaError_t spectrum_group2(const SpectrumLaunch &L, bool query, int *grid, int *spc);
+cudaError_t spectrum_group3(const SpectrumLaunch &L, bool query, int *grid, int *spc);
+
+// small helper kernels (spectrum.cu)
+void fill_f32(float *dst, size_t n, float v, cudaStream_t s);
+// peaks[i] = max(accumulate ? peaks[i] : -999999, max_s partial[s][i])
+void reduce_peaks(const float *partial, int slots, int N, float *peaks, bool accumulate, cudaStream_t s);
+// avg[i] = (sum_{r=0..L} row(newest + r*dir)[i]) / (L+1), rows past `valid` count as -9999
+void average_rows(const float *rows, long long newest, long long dir, long long ring_rows, long long row_stride,
+                  long long valid, int L, int N, float *avg, cudaStream_t s);
+// mean dB over bins [b0, b1) of each of nrows rows (FftProcessor.kt:150-156)
+void channel_strength(const float *rows, long long row0, long long row_step, long long ring_rows,
+                      long long row_stride, long long nrows, int b0, int b1, float *out, cudaStream_t s);
+// shift every ring row by `shift` bins, filling with -9999 (FftProcessor.kt:199-217)
+void shift_rows(float *rows, long long nrows, long long row_stride, int N, int shift, cudaStream_t s);
+
+}  // namespace rfa

@@ -1,0 +1,150 @@
+"""Batch objects over the C ABI: Context (device + stream) and SpectrumPlan (fused
+convert -> window -> FFT -> dB -> rows / peak hold / time average).
+
+Buffers may be torch CUDA tensors (device mode, asynchronous on the context's stream) or
+numpy arrays / CPU tensors (host mode, the library stages the copies).  One call uses one
+memory space for all its buffers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _is_device(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def _mem_of(*bufs):
+    kinds = {_is_device(b) for b in bufs if b is not None}
+    if len(kinds) > 1:
+        raise ValueError("all buffers of one call must live in the same memory space")
+    return _lib.MEM_DEVICE if kinds == {True} else _lib.MEM_HOST
+
+
+class Context:
+    """A GPU plus the CUDA stream every call of this context is ordered on."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        if stream is not None and hasattr(stream, "cuda_stream"):
+            # torch's default stream has handle 0 = the legacy default stream, which the C ABI
+            # spells cudaStreamLegacy ((cudaStream_t)1); NULL would mean "create a private stream"
+            stream = stream.cuda_stream or 1
+        check(self.lib.rfa_ctx_create(int(device), stream, C.byref(self.handle)))
+        self.device = int(device)
+
+    def close(self):
+        if self.handle:
+            self.lib.rfa_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.rfa_ctx_sync(self.handle))
+
+    @property
+    def sm_count(self):
+        return self.lib.rfa_ctx_sm_count(self.handle)
+
+    @property
+    def launch_count(self):
+        return self.lib.rfa_ctx_launch_count(self.handle)
+
+    # --- IQConverter.fillPacketIntoSamplePacket / mixPacketIntoSamplePacket -------------
+    def convert(self, fmt, iq, nsamples, re, im):
+        check(self.lib.rfa_convert(self.handle, fmt, ptr(iq), int(nsamples), ptr(re), ptr(im), _mem_of(iq, re, im)))
+
+    def nco_design(self, fmt, sample_rate, mix_frequency):
+        """generateMixerLookupTable: -> (effective_frequency, cos[len], sin[len])."""
+        eff, length = C.c_int(), C.c_int()
+        cos_t = np.zeros(500, np.float32)
+        sin_t = np.zeros(500, np.float32)
+        check(self.lib.rfa_nco_design(fmt, int(sample_rate), int(mix_frequency), C.byref(eff), C.byref(length),
+                                      ptr(cos_t), ptr(sin_t)))
+        return eff.value, cos_t[: length.value].copy(), sin_t[: length.value].copy()
+
+    def mix(self, fmt, iq, nsamples, cos_t, sin_t, nco_index, re, im):
+        cos_t = np.ascontiguousarray(cos_t, np.float32)
+        sin_t = np.ascontiguousarray(sin_t, np.float32)
+        check(self.lib.rfa_mix(self.handle, fmt, ptr(iq), int(nsamples), ptr(cos_t), ptr(sin_t), len(cos_t),
+                               int(nco_index), ptr(re), ptr(im), _mem_of(iq, re, im)))
+
+    # --- NativeDsp ------------------------------------------------------------------------
+    def make_window(self, window, n):
+        w = np.empty(n, np.float32)
+        check(self.lib.rfa_make_window(window, n, ptr(w)))
+        return w
+
+    def fft_c2c(self, x, out, n, batch=1):
+        check(self.lib.rfa_fft_c2c(self.handle, ptr(x), ptr(out), int(n), int(batch), _mem_of(x, out)))
+
+    def fft_logmag(self, x, mag, n, batch=1):
+        check(self.lib.rfa_fft_logmag(self.handle, ptr(x), ptr(mag), int(n), int(batch), _mem_of(x, mag)))
+
+    def windowed_fft_logmag(self, re, im, mag, n, batch=1, window=_lib.WIN_BLACKMAN_REF):
+        check(self.lib.rfa_windowed_fft_logmag(self.handle, ptr(re), ptr(im), ptr(mag), int(n), int(batch),
+                                               int(window), _mem_of(re, im, mag)))
+
+    # --- row reductions --------------------------------------------------------------------
+    def average_rows(self, rows, newest, direction, ring_rows, row_stride, valid, avg_len, n, avg):
+        check(self.lib.rfa_average_rows(self.handle, ptr(rows), int(newest), int(direction), int(ring_rows),
+                                        int(row_stride), int(valid), int(avg_len), int(n), ptr(avg),
+                                        _lib.MEM_DEVICE, _mem_of(avg)))
+
+    def channel_bins(self, n, frequency, sample_rate, chan_start, chan_end):
+        b0, b1 = C.c_int(), C.c_int()
+        check(self.lib.rfa_channel_bins(int(n), int(frequency), int(sample_rate), int(chan_start), int(chan_end),
+                                        C.byref(b0), C.byref(b1)))
+        return b0.value, b1.value
+
+    def channel_strength(self, rows, row0, row_step, ring_rows, row_stride, nrows, b0, b1, out):
+        check(self.lib.rfa_channel_strength(self.handle, ptr(rows), int(row0), int(row_step), int(ring_rows),
+                                            int(row_stride), int(nrows), int(b0), int(b1), ptr(out), _mem_of(out)))
+
+    def shift_rows(self, rows, nrows, row_stride, n, shift):
+        check(self.lib.rfa_shift_rows(self.handle, ptr(rows), int(nrows), int(row_stride), int(n), int(shift)))
+
+    def fill(self, dst, count, value):
+        check(self.lib.rfa_fill(self.handle, ptr(dst), int(count), float(value)))
+
+
+class SpectrumPlan:
+    """Fused IQ bytes -> dB waterfall rows (+ peak hold + time average) for one FFT size."""
+
+    def __init__(self, ctx, fmt, fft_size, window=_lib.WIN_BLACKMAN_REF, avg_len=0, peak_hold=True):
+        self.ctx = ctx
+        self.fmt, self.fft_size, self.avg_len = fmt, int(fft_size), int(avg_len)
+        self.desc = _lib.SpectrumDesc(fmt, int(fft_size), int(window), int(avg_len), 1 if peak_hold else 0)
+        self.handle = C.c_void_p()
+        check(ctx.lib.rfa_spectrum_plan_create(ctx.handle, C.byref(self.desc), C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.rfa_spectrum_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def algorithmic_bytes(self, nframes, rows_stored=True):
+        return self.ctx.lib.rfa_spectrum_algorithmic_bytes(self.handle, int(nframes), 1 if rows_stored else 0)
+
+    def process(self, iq, nframes, rows=None, peaks=None, avg=None, row0=0, row_step=1, ring_rows=0,
+                row_stride=None, history_rows=0, peaks_accumulate=False):
+        out = _lib.SpectrumOut(ptr(rows), int(row0), int(row_step), int(ring_rows),
+                               int(row_stride if row_stride is not None else self.fft_size), int(history_rows),
+                               ptr(peaks), 1 if peaks_accumulate else 0, ptr(avg))
+        check(self.ctx.lib.rfa_spectrum_process(self.handle, ptr(iq), int(nframes), C.byref(out),
+                                                _mem_of(iq, rows, peaks, avg)))

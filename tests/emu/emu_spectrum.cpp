@@ -1,0 +1,156 @@
+// emu_spectrum.cpp -- CPU emulation of the fused spectrum kernel (test support).
+//
+// There is no GPU in the build container, so the kernel's per-thread phase functions
+// (rfanalyzer_b200/csrc/spectrum_kernel.cuh, all __host__ __device__) are run here thread
+// by thread, with loop boundaries standing in for __syncthreads().  This exercises the exact
+// index arithmetic, twiddle addressing, butterflies, conversion and dB scaling the GPU runs.
+// It is NOT a product path: nothing in rfanalyzer_b200 loads it.
+#include <array>
+#include <cstring>
+#include <vector>
+
+#include "../../rfanalyzer_b200/csrc/rfa_tables.h"
+#include "../../rfanalyzer_b200/csrc/spectrum_kernel.cuh"
+
+using namespace rfa;
+
+namespace {
+
+template <int NL, int S, int IN, int OUT, int PASS>
+struct EmuPasses {
+    using F = SpectrumFrame<NL, S, IN, OUT>;
+    using TwRegs = std::vector<std::array<cf, (F::LAST_TW_REG ? F::LAST_TW : 1)>>;
+    static void run(std::vector<cf> &x, const cf *tw, TwRegs &TWR, std::vector<std::array<cf, Geom<NL>::E>> &U) {
+        constexpr int T = Geom<NL>::T;
+        if constexpr (PASS < Plan<NL>::PASSES) {
+            for (int tid = 0; tid < T; tid++) F::template scatter<PASS - 1>(x.data(), tid, U[tid].data());
+            for (int tid = 0; tid < T; tid++) {
+                if constexpr (PASS == F::LAST && F::LAST_TW_REG)
+                    F::gather_last_reg(x.data(), TWR[tid].data(), tid, U[tid].data());
+                else
+                    F::template gather<PASS>(x.data(), tw, tid, U[tid].data());
+            }
+            EmuPasses<NL, S, IN, OUT, PASS + 1>::run(x, tw, TWR, U);
+        }
+    }
+};
+
+template <int NL, int S, int IN, int OUT>
+int emu_one(SpectrumParams p, float *peaks) {
+    using G = Geom<NL>;
+    using F = SpectrumFrame<NL, S, IN, OUT>;
+    constexpr int T = G::T, E = G::E, N = NL * S;
+    std::vector<cf> tw = make_pass_twiddles(NL), twN(N);
+    make_twiddles(N, twN.data());
+    p.tw = tw.data();
+    p.twN = twN.data();
+    p.inv_n2 = 1.0f / ((float)N * (float)N);
+    std::vector<cf> x(Plan<NL>::SMEM_POINTS);
+    std::vector<std::array<cf, E>> U(T);
+    std::vector<std::array<float, E>> PK((size_t)T * S);
+    for (auto &a : PK) a.fill(-999999.0f);
+    std::vector<std::array<float, E>> W(T);
+    if (S == 1) {
+        constexpr int R = Plan<NL>::radix(0), STR = NL / R;
+        for (int tid = 0; tid < T; tid++)
+            for (int b = 0; b < E / R; b++)
+                for (int r = 0; r < R; r++)
+                    W[tid][b * R + r] = (p.win ? p.win[tid + b * T + r * STR] : 1.0f) * unit_scale<IN>();
+    }
+    std::vector<std::array<cf, (F::LAST_TW_REG ? F::LAST_TW : 1)>> TWR(T);
+    if constexpr (F::LAST_TW_REG)
+        for (int tid = 0; tid < T; tid++) F::load_last_tw(tw.data(), tid, TWR[tid].data());
+    std::vector<std::array<uint32_t, E>> RAW(T);
+    for (long long f = 0; f < p.nframes; f++)
+        for (int c = 0; c < S; c++) {
+            for (int tid = 0; tid < T; tid++) {
+                if constexpr (F::PREFETCH) {
+                    F::load_raw((const char *)p.in + (f * (long long)N + tid) * in_elem_bytes<IN>(), RAW[tid].data());
+                    F::first_from_raw(RAW[tid].data(), W[tid].data(), U[tid].data());
+                } else {
+                    F::first(p, f, c, tid, W[tid].data(), U[tid].data());
+                }
+            }
+            if constexpr (Plan<NL>::PASSES > 1) EmuPasses<NL, S, IN, OUT, 1>::run(x, tw.data(), TWR, U);
+            for (int tid = 0; tid < T; tid++) {
+                float *out = p.rows + frame_row(p, f) * p.row_stride;
+                if (OUT == OUT_DB && peaks)
+                    F::template emit<true, true>(out, c, tid, U[tid].data(), PK[(size_t)c * T + tid].data(), p.inv_n2);
+                else
+                    F::template emit<false, true>(out, c, tid, U[tid].data(), nullptr, p.inv_n2);
+            }
+        }
+    if (OUT == OUT_DB && peaks) {
+        for (int i = 0; i < N; i++) peaks[i] = -999999.0f;
+        for (int c = 0; c < S; c++)
+            for (int tid = 0; tid < T; tid++)
+                for (int e = 0; e < E; e++) {
+                    float &dst = peaks[F::peak_index(c, tid, e)];
+                    dst = dst > PK[(size_t)c * T + tid][e] ? dst : PK[(size_t)c * T + tid][e];
+                }
+    }
+    if (OUT == OUT_DB && p.avg)
+        for (int i = 0; i < N; i++) p.avg[i] = boxcar_average(p, i, [](const float *a) { return *a; });
+    return 0;
+}
+
+template <int NL, int S>
+int emu_size(int in_fmt, int out_kind, const SpectrumParams &p, float *peaks) {
+    if (out_kind == OUT_CPLX) return in_fmt == FMT_CF32 ? emu_one<NL, S, FMT_CF32, OUT_CPLX>(p, peaks) : -1;
+    switch (in_fmt) {
+        case FMT_S8: return emu_one<NL, S, FMT_S8, OUT_DB>(p, peaks);
+        case FMT_U8: return emu_one<NL, S, FMT_U8, OUT_DB>(p, peaks);
+        case FMT_S16LE: return emu_one<NL, S, FMT_S16LE, OUT_DB>(p, peaks);
+        case FMT_CF32: return emu_one<NL, S, FMT_CF32, OUT_DB>(p, peaks);
+        case FMT_PF32: return emu_one<NL, S, FMT_PF32, OUT_DB>(p, peaks);
+    }
+    return -1;
+}
+
+}  // namespace
+
+extern "C" int emu_spectrum_avg(int N, int in_fmt, int out_kind, int window_kind /* -1: none */, const void *in,
+                                const float *in_im, long long nframes, float *rows, float *peaks, float *avg, int L) {
+    SpectrumParams p{};
+    std::vector<float> win;
+    if (window_kind >= 0) {
+        win.resize(N);
+        make_window(window_kind, N, win.data());
+        p.win = win.data();
+    }
+    p.in = in;
+    p.in_im = in_im;
+    p.rows = rows;
+    p.row0 = 0;
+    p.row_step = 1;
+    p.ring_rows = 0;
+    p.row_stride = out_kind == OUT_CPLX ? 2LL * N : N;
+    p.nframes = nframes;
+    p.store_from = 0;
+    p.avg = avg;
+    p.avg_len = L;
+    p.avg_newest = nframes - 1;
+    p.avg_dir = -1;
+    p.avg_valid = nframes;
+    switch (N) {
+        case 16: return emu_size<16, 1>(in_fmt, out_kind, p, peaks);
+        case 32: return emu_size<32, 1>(in_fmt, out_kind, p, peaks);
+        case 64: return emu_size<64, 1>(in_fmt, out_kind, p, peaks);
+        case 128: return emu_size<128, 1>(in_fmt, out_kind, p, peaks);
+        case 256: return emu_size<256, 1>(in_fmt, out_kind, p, peaks);
+        case 512: return emu_size<512, 1>(in_fmt, out_kind, p, peaks);
+        case 1024: return emu_size<1024, 1>(in_fmt, out_kind, p, peaks);
+        case 2048: return emu_size<2048, 1>(in_fmt, out_kind, p, peaks);
+        case 4096: return emu_size<4096, 1>(in_fmt, out_kind, p, peaks);
+        case 8192: return emu_size<8192, 1>(in_fmt, out_kind, p, peaks);
+        case 16384: return emu_size<16384, 1>(in_fmt, out_kind, p, peaks);
+        case 32768: return emu_size<16384, 2>(in_fmt, out_kind, p, peaks);
+        case 65536: return emu_size<16384, 4>(in_fmt, out_kind, p, peaks);
+    }
+    return -1;
+}
+
+extern "C" int emu_spectrum(int N, int in_fmt, int out_kind, int window_kind, const void *in, const float *in_im,
+                            long long nframes, float *rows, float *peaks) {
+    return emu_spectrum_avg(N, in_fmt, out_kind, window_kind, in, in_im, nframes, rows, peaks, nullptr, 0);
+}
