@@ -155,6 +155,22 @@ int rfa_channel_strength(rfa_ctx *ctx, const float *rows, long long row0, long l
 int rfa_shift_rows(rfa_ctx *ctx, float *rows, long long nrows, long long row_stride, int n, int shift);
 int rfa_fill(rfa_ctx *ctx, float *dst, long long count, float value);
 
+/* ---- synthetic IQ (benchmark / test input; the reference ships no input fixtures) ------ */
+/* All-integer generator of SURVEY.md 8(d): sample n depends on n alone, so any segment of a
+ * long recording can be produced in place on any GPU.
+ *   h = fmix32(seed ^ (u32)n ^ ((u32)(n>>32) * 0x9E3779B9)); noise = signed low bytes/halves >> noise_shift
+ *   component k: phase = (u32)(n*step) + (u32)(mod_k * tab[((u32)(n*mod_step) - 2^30) >> 20]),
+ *                I += (amp*tab[phase>>20] + 8192) >> 14, Q likewise with phase - 2^30,
+ *   tab[j] = lround(16384*cos(2*pi*j/4096)); u8 adds 128; s16 is little endian. */
+typedef struct {
+    uint32_t step;     /* tone frequency, cycles/sample * 2^32 */
+    int32_t amp;       /* LSB */
+    uint32_t mod_step; /* FM: modulating tone, cycles/sample * 2^32 */
+    int32_t mod_k;     /* FM: peak phase deviation / (2*pi) * 2^32 / 16384; 0 = plain tone */
+} rfa_synth_comp;
+int rfa_synth_iq(rfa_ctx *ctx, int fmt, uint32_t seed, const rfa_synth_comp *comps, int ncomp, int noise_shift,
+                 long long first_sample, long long nsamples, void *out, int mem);
+
 #ifdef __cplusplus
 }
 #endif

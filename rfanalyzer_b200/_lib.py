@@ -36,6 +36,10 @@ class SpectrumOut(C.Structure):
                 ("peaks", C.c_void_p), ("peaks_accumulate", C.c_int), ("avg", C.c_void_p)]
 
 
+class SynthComp(C.Structure):
+    _fields_ = [("step", C.c_uint32), ("amp", C.c_int32), ("mod_step", C.c_uint32), ("mod_k", C.c_int32)]
+
+
 class ChainDesc(C.Structure):
     _fields_ = [("format", C.c_int), ("sample_rate", C.c_int), ("source_frequency", C.c_longlong),
                 ("channel_frequency", C.c_longlong), ("mode", C.c_int), ("channel_width", C.c_int),
@@ -75,6 +79,7 @@ SIGNATURES = {
     "rfa_channel_strength": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _vp, _i]),
     "rfa_shift_rows": (_i, [_vp, _vp, _ll, _ll, _i, _i]),
     "rfa_fill": (_i, [_vp, _vp, _ll, _f]),
+    "rfa_synth_iq": (_i, [_vp, _i, C.c_uint32, C.POINTER(SynthComp), _i, _i, _ll, _ll, _vp, _i]),
 }
 
 _LIB = None

@@ -154,6 +154,7 @@ int rfa_ctx_destroy(rfa_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->twiddles) cudaFree(kv.second);
     for (auto &kv : c->windows) cudaFree(kv.second);
+    if (c->synth_table) cudaFree(c->synth_table);
     for (auto &b : c->stage) b.release();
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(c->ev_in[i]);
@@ -637,6 +638,42 @@ int rfa_shift_rows(rfa_ctx *c, float *rows, long long nrows, long long row_strid
     shift_rows(rows, nrows, row_stride, n, shift, c->stream);
     RFA_CK(cudaGetLastError());
     c->launches++;
+    return RFA_OK;
+}
+
+int rfa_synth_iq(rfa_ctx *c, int fmt, uint32_t seed, const rfa_synth_comp *comps, int ncomp, int noise_shift,
+                 long long first_sample, long long nsamples, void *out, int mem) {
+    RFA_REQUIRE(c && out, "rfa_synth_iq: NULL argument");
+    RFA_REQUIRE(fmt >= RFA_FMT_S8 && fmt <= RFA_FMT_S16LE, "unknown sample format %d", fmt);
+    RFA_REQUIRE(ncomp >= 0 && ncomp <= 8 && (ncomp == 0 || comps), "0..8 components");
+    RFA_REQUIRE(noise_shift >= 0 && noise_shift < 16 && first_sample >= 0 && nsamples >= 0, "bad generator range");
+    if (nsamples == 0) return RFA_OK;
+    if (int rc = c->use()) return rc;
+    if (!c->synth_table) {
+        short host[4096];
+        synth_make_table(host);
+        RFA_CK(cudaMalloc(&c->synth_table, sizeof(host)));
+        RFA_CK(cudaMemcpyAsync(c->synth_table, host, sizeof(host), cudaMemcpyHostToDevice, c->stream));
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    }
+    SynthComp cc[8];
+    for (int i = 0; i < ncomp; i++) cc[i] = SynthComp{comps[i].step, comps[i].amp, comps[i].mod_step, comps[i].mod_k};
+    const size_t bytes = (size_t)nsamples * fmt_bytes(fmt);
+    void *dout = out;
+    if (mem == RFA_MEM_HOST) {
+        if (int rc = c->stage[0].ensure(bytes)) return rc;
+        dout = c->stage[0].p;
+    } else {
+        RFA_REQUIRE(((uintptr_t)out & 3) == 0, "device output must be 4-byte aligned");
+    }
+    cudaError_t e = synth_launch(fmt, seed, cc, ncomp, noise_shift, (unsigned long long)first_sample, nsamples,
+                                 c->synth_table, dout, c->num_sms, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "synth kernel");
+    c->launches++;
+    if (mem == RFA_MEM_HOST) {
+        RFA_CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, c->stream));
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    }
     return RFA_OK;
 }
 

@@ -58,6 +58,7 @@ struct rfa_ctx {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     std::map<int, rfa::cf *> twiddles;                // per transform size
     std::map<std::pair<int, int>, float *> windows;   // per (kind, size)
+    short *synth_table = nullptr;                     // generator's cosine table
     rfa::Buf stage[8];                                // staging for RFA_MEM_HOST calls
     int get_twiddles(int n, const rfa::cf **out);
     int get_window(int kind, int n, const float **out);

@@ -117,6 +117,33 @@ class Context:
         check(self.lib.rfa_fill(self.handle, ptr(dst), int(count), float(value)))
 
 
+SYNTH_SEED = 0x52464131
+
+
+def synth_step(cycles_per_sample):
+    """Tone frequency as a 32-bit phase increment (cycles/sample, negative allowed)."""
+    frac = cycles_per_sample - np.floor(cycles_per_sample)
+    return int(round(frac * 4294967296.0)) & 0xFFFFFFFF
+
+
+def default_synth_components(fmt):
+    """The three-tone spectrum-path signal of SURVEY.md 8(d): (f/fs, amplitude) =
+    (+0.1234, 48), (-0.3071, 24), (+0.0127, 12) LSB, x256 for 16-bit samples."""
+    mul = 256 if fmt == _lib.FMT_S16LE else 1
+    return [(synth_step(0.1234), 48 * mul, 0, 0), (synth_step(-0.3071), 24 * mul, 0, 0),
+            (synth_step(0.0127), 12 * mul, 0, 0)]
+
+
+def synth_iq(ctx, fmt, nsamples, out, first=0, comps=None, noise_shift=2, seed=SYNTH_SEED):
+    """Fill `out` (device tensor or host array of bytes) with samples first .. first+nsamples-1."""
+    comps = default_synth_components(fmt) if comps is None else comps
+    arr = (_lib.SynthComp * max(len(comps), 1))()
+    for i, c in enumerate(comps):
+        arr[i] = _lib.SynthComp(*[int(v) for v in c])
+    check(ctx.lib.rfa_synth_iq(ctx.handle, fmt, seed, arr, len(comps), int(noise_shift), int(first), int(nsamples),
+                               ptr(out), _mem_of(out)))
+
+
 class SpectrumPlan:
     """Fused IQ bytes -> dB waterfall rows (+ peak hold + time average) for one FFT size."""
 

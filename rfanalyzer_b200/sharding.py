@@ -1,0 +1,84 @@
+"""Time-sharding of a long IQ recording across GPUs.
+
+FFT frames do not overlap (Scheduler.kt:254-276), so a recording of F frames is cut into
+contiguous time segments, one per rank, with no halo and no data-path collective.  Only the
+two N-float summaries are exchanged at the end of a pass:
+
+  * peak hold  -- element-wise max over all rows (FftProcessor.kt:244)  -> all_reduce(MAX)
+  * time average of the newest L+1 rows (AnalyzerSurface.kt:710-714) -> the newest rows live
+    on the last rank(s); normally the last rank alone holds all L+1 and broadcasts its result,
+    otherwise the ranks' newest rows are gathered and summed in the reference's order.
+
+`torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests) is the plumbing.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_frames(total_frames, world_size, rank):
+    """Contiguous segment of rank `rank`: (first_frame, nframes); earlier ranks get the remainder."""
+    base, rem = divmod(int(total_frames), int(world_size))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def tail_owner_plan(total_frames, world_size, avg_len):
+    """Which ranks hold the newest avg_len+1 rows: list of (rank, rows_taken), newest first."""
+    need = min(avg_len + 1, int(total_frames))
+    plan = []
+    for r in range(world_size - 1, -1, -1):
+        if need == 0:
+            break
+        _, n = shard_frames(total_frames, world_size, r)
+        take = min(n, need)
+        if take:
+            plan.append((r, take))
+            need -= take
+    return plan
+
+
+def assemble_tail(gathered, total_frames, world_size, avg_len, fill=-9999.0):
+    """gathered[r]: [avg_len+1, N] with rank r's newest rows, newest first.  Returns the global
+    newest avg_len+1 rows, newest first; rows that do not exist hold -9999f (FftProcessor.kt:181)."""
+    n = gathered[0].shape[-1]
+    out = torch.full((avg_len + 1, n), fill, dtype=gathered[0].dtype, device=gathered[0].device)
+    k = 0
+    for r, take in tail_owner_plan(total_frames, world_size, avg_len):
+        out[k:k + take] = gathered[r][:take]
+        k += take
+    return out
+
+
+class ShardedSpectrum:
+    """One rank's share of a time-sharded spectrum pass plus the summary reduction."""
+
+    def __init__(self, plan, rank=0, world_size=1, group=None):
+        self.plan, self.rank, self.world, self.group = plan, rank, world_size, group
+        self.n, self.L = plan.fft_size, plan.avg_len
+
+    def local_range(self, total_frames):
+        return shard_frames(total_frames, self.world, self.rank)
+
+    def process(self, iq_local, total_frames, rows_local, peaks, avg, peaks_accumulate=False):
+        """iq_local / rows_local: this rank's segment; peaks / avg: [N] device tensors that hold
+        the GLOBAL result on every rank afterwards."""
+        _, nloc = self.local_range(total_frames)
+        self.plan.process(iq_local, nloc, rows=rows_local, peaks=peaks, avg=avg, peaks_accumulate=peaks_accumulate)
+        if self.world == 1:
+            return
+        if nloc == 0 and not peaks_accumulate:
+            peaks.fill_(-999999.0)
+        dist.all_reduce(peaks, op=dist.ReduceOp.MAX, group=self.group)
+        owners = tail_owner_plan(total_frames, self.world, self.L)
+        if len(owners) == 1 and owners[0][1] == min(self.L + 1, total_frames) and total_frames >= self.L + 1:
+            dist.broadcast(avg, src=owners[0][0], group=self.group)
+            return
+        # rare: the newest L+1 rows straddle ranks -- gather each rank's newest rows
+        mine = torch.full((self.L + 1, self.n), -9999.0, dtype=torch.float32, device=avg.device)
+        take = min(self.L + 1, nloc)
+        if take:
+            mine[:take] = torch.flip(rows_local[nloc - take:nloc, : self.n], dims=[0])
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=self.group)
+        tail = assemble_tail(gathered, total_frames, self.world, self.L).contiguous()
+        self.plan.ctx.average_rows(tail, 0, 1, 0, self.n, min(self.L + 1, total_frames), self.L, self.n, avg)
