@@ -155,6 +155,80 @@ int rfa_channel_strength(rfa_ctx *ctx, const float *rows, long long row0, long l
 int rfa_shift_rows(rfa_ctx *ctx, float *rows, long long nrows, long long row_stride, int n, int shift);
 int rfa_fill(rfa_ctx *ctx, float *dst, long long count, float value);
 
+/* ---- filter design (host functions; float/double usage follows the reference) ---------- */
+/* WindowFunction.value (A/dsp/WindowFunctions.kt:44-100) */
+int rfa_tap_window(int kind, double beta, int n, int N, float *out);
+/* FirFilter.createLowPassTaps (A/dsp/FirFilter.kt:182-241).  taps may be NULL to query ntaps. */
+int rfa_design_lowpass(float gain, float sample_rate, float cutoff, float transition_width, float attenuation_db,
+                       int window, double beta, int max_taps, float *taps, int capacity, int *ntaps);
+/* ComplexFirFilter.createBandPass (A/dsp/ComplexFirFilter.java:186-262) */
+int rfa_design_bandpass(float gain, float sample_rate, float low_cutoff, float high_cutoff, float transition_width,
+                        float attenuation_db, float *taps_re, float *taps_im, int capacity, int *ntaps);
+/* RationalResampler.limitDenominator / designResamplerTaps (A/dsp/RationalResampler.kt:183-255) */
+int rfa_limit_denominator(int numerator, int denominator, int max_denominator, int *out_num, int *out_den);
+int rfa_design_resampler_taps(int interpolation, int decimation, float fractional_bw, int max_taps, float *taps,
+                              int capacity, int *ntaps);
+
+/* ---- FirFilter / ComplexFirFilter (A/dsp/FirFilter.kt:34-163, ComplexFirFilter.java:33-170) -
+ * Streaming objects: state (delay line, decimationCounter starting at 1) persists across
+ * calls exactly like the reference's fields.  taps_im != NULL makes it a ComplexFirFilter.
+ * process(): in_im == NULL is filterReal.  Appends nothing itself: out_* receive *n_out
+ * samples (at most out_capacity); *consumed follows the reference's return value (less than
+ * n only when the output ran full). */
+int rfa_fir_create(rfa_ctx *ctx, const float *taps_re, const float *taps_im, int ntaps, int decimation, int flags,
+                   rfa_fir **out);
+int rfa_fir_destroy(rfa_fir *fir);
+int rfa_fir_reset(rfa_fir *fir);
+int rfa_fir_process(rfa_fir *fir, const float *in_re, const float *in_im, long long n, float *out_re,
+                    float *out_im, long long out_capacity, long long *n_out, long long *consumed, int mem);
+
+/* ---- RationalResampler (A/dsp/RationalResampler.kt:36-156) -------------------------------
+ * taps == NULL designs them (designResamplerTaps, Kaiser beta 7).  I/D are reduced by
+ * their gcd like the constructor does. */
+int rfa_resampler_create(rfa_ctx *ctx, int interpolation, int decimation, const float *taps, int ntaps,
+                         float fractional_bw, int max_taps, int flags, rfa_resampler **out);
+int rfa_resampler_destroy(rfa_resampler *rs);
+int rfa_resampler_info(const rfa_resampler *rs, int *interpolation, int *decimation, int *taps_per_phase);
+int rfa_resampler_process(rfa_resampler *rs, const float *in_re, const float *in_im, long long n, float *out_re,
+                          float *out_im, long long out_capacity, long long *n_out, long long *consumed, int mem);
+
+/* ---- Demodulator stages (A/analyzer/Demodulator.kt:251-403), one packet per call ---------- */
+/* demodulateFM: carry[2] (host, in/out) = last sample of the previous packet; the result is
+ * multiplied by `volume` (Demodulator.run :184-187). */
+int rfa_demod_fm(rfa_ctx *ctx, const float *re, const float *im, long long n, float *carry,
+                 float quadrature_gain, float volume, float *out, int flags, int mem);
+/* demodulateAM: |x|^2, minus the packet mean, times 0.75/lastMax; *last_max (host) in/out. */
+int rfa_demod_am(rfa_ctx *ctx, const float *re, const float *im, long long n, float *last_max, float volume,
+                 float *out, int flags, int mem);
+/* the gain control at the end of demodulateSSB / demodulateCW, in place on x */
+int rfa_agc(rfa_ctx *ctx, float *x, long long n, float *last_max, float volume, int flags, int mem);
+/* mode table: quadrature rate (Demodulator.kt:53-62) and channel widths (DemodulationTab.kt:90-99) */
+int rfa_mode_info(int mode, int *quadrature_rate, int *min_width, int *max_width, int *default_width);
+
+/* ---- the whole IQ -> audio chain ------------------------------------------------------------
+ * Scheduler.kt:237-244 (mixPacketIntoSamplePacket) -> Resampler.kt:95-113 -> Demodulator.kt:147-187
+ * (user filter, demodulator, volume) -> AudioSink.java:182-187 (decimation to 48 kHz), every packet
+ * delivered.  State carries across calls; every call but the last must be a whole number of packets. */
+typedef struct {
+    int format;                  /* RFA_FMT_* */
+    int sample_rate;             /* source sample rate, Hz */
+    long long source_frequency;  /* IQSource frequency */
+    long long channel_frequency; /* Scheduler.channelFrequency (CW: caller adds the 750 Hz offset, AnalyzerService.kt:439-442) */
+    int mode;                    /* RFA_MODE_AM .. RFA_MODE_CW */
+    int channel_width;           /* Hz, coerced to the mode's range; 0 = the mode's default */
+    int packet_samples;          /* source.packetSize / bytesPerSample (AnalyzerService.kt:324-328) */
+    float volume;                /* audioVolumeLevel */
+    int flags;                   /* RFA_SUM_FMA / RFA_SUM_EXACT */
+} rfa_chain_desc;
+int rfa_chain_create(rfa_ctx *ctx, const rfa_chain_desc *desc, rfa_chain **out);
+int rfa_chain_destroy(rfa_chain *chain);
+int rfa_chain_info(const rfa_chain *chain, int *interpolation, int *decimation, int *taps_per_phase,
+                   int *quadrature_rate, int *channel_width, int *nco_length, int *nco_frequency);
+/* audio buffer capacity (samples) that rfa_chain_process needs for nsamples inputs */
+long long rfa_chain_max_audio(const rfa_chain *chain, long long nsamples);
+int rfa_chain_process(rfa_chain *chain, const void *iq, long long nsamples, float *audio, long long capacity,
+                      long long *n_audio, int mem);
+
 /* ---- synthetic IQ (benchmark / test input; the reference ships no input fixtures) ------ */
 /* All-integer generator of SURVEY.md 8(d): sample n depends on n alone, so any segment of a
  * long recording can be produced in place on any GPU.

@@ -79,6 +79,28 @@ SIGNATURES = {
     "rfa_channel_strength": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _vp, _i]),
     "rfa_shift_rows": (_i, [_vp, _vp, _ll, _ll, _i, _i]),
     "rfa_fill": (_i, [_vp, _vp, _ll, _f]),
+    "rfa_tap_window": (_i, [_i, _d, _i, _i, C.POINTER(C.c_float)]),
+    "rfa_design_lowpass": (_i, [_f, _f, _f, _f, _f, _i, _d, _i, _vp, _i, _pi]),
+    "rfa_design_bandpass": (_i, [_f, _f, _f, _f, _f, _f, _vp, _vp, _i, _pi]),
+    "rfa_limit_denominator": (_i, [_i, _i, _i, _pi, _pi]),
+    "rfa_design_resampler_taps": (_i, [_i, _i, _f, _i, _vp, _i, _pi]),
+    "rfa_fir_create": (_i, [_vp, _vp, _vp, _i, _i, _i, _pvp]),
+    "rfa_fir_destroy": (_i, [_vp]),
+    "rfa_fir_reset": (_i, [_vp]),
+    "rfa_fir_process": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _pll, _pll, _i]),
+    "rfa_resampler_create": (_i, [_vp, _i, _i, _vp, _i, _f, _i, _i, _pvp]),
+    "rfa_resampler_destroy": (_i, [_vp]),
+    "rfa_resampler_info": (_i, [_vp, _pi, _pi, _pi]),
+    "rfa_resampler_process": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _pll, _pll, _i]),
+    "rfa_demod_fm": (_i, [_vp, _vp, _vp, _ll, _vp, _f, _f, _vp, _i, _i]),
+    "rfa_demod_am": (_i, [_vp, _vp, _vp, _ll, _vp, _f, _vp, _i, _i]),
+    "rfa_agc": (_i, [_vp, _vp, _ll, _vp, _f, _i, _i]),
+    "rfa_mode_info": (_i, [_i, _pi, _pi, _pi, _pi]),
+    "rfa_chain_create": (_i, [_vp, C.POINTER(ChainDesc), _pvp]),
+    "rfa_chain_destroy": (_i, [_vp]),
+    "rfa_chain_info": (_i, [_vp, _pi, _pi, _pi, _pi, _pi, _pi, _pi]),
+    "rfa_chain_max_audio": (_ll, [_vp, _ll]),
+    "rfa_chain_process": (_i, [_vp, _vp, _ll, _vp, _ll, _pll, _i]),
     "rfa_synth_iq": (_i, [_vp, _i, C.c_uint32, C.POINTER(SynthComp), _i, _i, _ll, _ll, _vp, _i]),
 }
 

@@ -9,6 +9,30 @@ cudaError_t convert_launch(int fmt, const void *iq, long long n, float *re, floa
 cudaError_t mix_launch(int fmt, const void *iq, long long n, float *re, float *im, const float *cosT,
                        const float *sinT, int len, int idx, int num_sms, cudaStream_t st);
 
+// a sample stream as the FIR / resampler kernels see it: index 0 is the first sample of this
+// call, negative indices come from the `hist` samples carried over from earlier calls
+struct StreamDesc {
+    int kind = 3;                       // 0..2: raw IQ codes (FMT_*), converted (and mixed) on load; 3: planar floats
+    const float *re = nullptr, *im = nullptr;
+    const void *raw = nullptr;
+    const float *hist_re = nullptr, *hist_im = nullptr;
+    int hist = 0;
+    const float *nco_cos = nullptr, *nco_sin = nullptr;  // device tables; nullptr = no mixing
+    int nco_len = 1, nco_idx = 0;
+};
+cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int D, int nt, long long rel, int ph0,
+                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st);
+cudaError_t fir_launch(const StreamDesc &in, const float *taps_re, const float *taps_im, int ntaps, int dec,
+                       long long first, long long nout, bool real_only, float *out_re, float *out_im, bool exact,
+                       cudaStream_t st);
+cudaError_t history_launch(const StreamDesc &in, long long consumed, float *new_re, float *new_im, cudaStream_t st);
+cudaError_t demod_fm_launch(const float *re, const float *im, long long n, float *carry, float gain, float volume,
+                            float *out, bool exact, int num_sms, cudaStream_t st);
+cudaError_t demod_power_launch(const float *re, const float *im, long long n, float *out, int num_sms,
+                               cudaStream_t st);
+cudaError_t agc_launch(float *x, const long long *off, int npackets, long long max_packet, bool subtract_mean,
+                       float *state, float *scratch, float volume, bool exact, int num_sms, cudaStream_t st);
+
 struct SynthComp {
     unsigned int step;
     int amp;
