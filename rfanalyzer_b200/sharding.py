@@ -59,18 +59,27 @@ class ShardedSpectrum:
     def local_range(self, total_frames):
         return shard_frames(total_frames, self.world, self.rank)
 
-    def process(self, iq_local, total_frames, rows_local, peaks, avg, peaks_accumulate=False):
-        """iq_local / rows_local: this rank's segment; peaks / avg: [N] device tensors that hold
-        the GLOBAL result on every rank afterwards."""
+    def process(self, iq_local, total_frames, rows_local, peaks, avg, peaks_accumulate=False, reduce=True):
+        """iq_local / rows_local: this rank's segment; peaks / avg: [N] device tensors.  With
+        reduce=True they hold the GLOBAL result on every rank afterwards; with reduce=False they
+        hold this rank's running summaries and reduce() is called once when the recording ends
+        (the peak hold and the averaged spectrum are properties of the whole recording)."""
         _, nloc = self.local_range(total_frames)
         self.plan.process(iq_local, nloc, rows=rows_local, peaks=peaks, avg=avg, peaks_accumulate=peaks_accumulate)
-        if self.world == 1:
-            return
         if nloc == 0 and not peaks_accumulate:
             peaks.fill_(-999999.0)
+        if reduce:
+            self.reduce(total_frames, rows_local, peaks, avg)
+
+    def reduce(self, total_frames, rows_local, peaks, avg):
+        """Exchange the two N-float summaries: all_reduce(MAX) of the peak hold, and the average of
+        the newest L+1 rows from the rank(s) that hold them."""
+        if self.world == 1:
+            return
+        _, nloc = self.local_range(total_frames)
         dist.all_reduce(peaks, op=dist.ReduceOp.MAX, group=self.group)
         owners = tail_owner_plan(total_frames, self.world, self.L)
-        if len(owners) == 1 and owners[0][1] == min(self.L + 1, total_frames) and total_frames >= self.L + 1:
+        if len(owners) == 1 and total_frames >= self.L + 1:
             dist.broadcast(avg, src=owners[0][0], group=self.group)
             return
         # rare: the newest L+1 rows straddle ranks -- gather each rank's newest rows
