@@ -103,26 +103,36 @@ void channel_strength(const float *rows, long long row0, long long row_step, lon
 }
 
 // FftProcessor.kt:199-217: after a retune every history row moves by `shift` bins
-// (shift < 0: left) and the vacated bins become -9999f.  One CTA per row stages the row
-// in shared memory so the move is safe in place.
-__global__ void shift_rows_kernel(float *rows, long long row_stride, int N, int shift) {
-    extern __shared__ float srow[];
+// (shift < 0: left) and the vacated bins become -9999f.  One CTA per row moves it IN PLACE in
+// chunks of 1024 bins, walking against the shift direction: a chunk is loaded completely
+// before it is stored, and its destination only overlaps bins that were already moved.
+__global__ void __launch_bounds__(256) shift_rows_kernel(float *rows, long long row_stride, int N, int shift) {
     float *p = rows + (long long)blockIdx.x * row_stride;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) srow[i] = p[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        int src = i - shift;
-        p[i] = (src >= 0 && src < N) ? srow[src] : -9999.0f;
+    const int chunks = (N + 1023) / 1024;
+    for (int cc = 0; cc < chunks; cc++) {
+        const int c = shift > 0 ? chunks - 1 - cc : cc;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int src = c * 1024 + j * 256 + threadIdx.x;
+            v[j] = src < N ? p[src] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int src = c * 1024 + j * 256 + threadIdx.x, dst = src + shift;
+            if (src < N && dst >= 0 && dst < N) p[dst] = v[j];
+        }
+        __syncthreads();
     }
+    // vacated bins
+    const int lo = shift > 0 ? 0 : (N + shift > 0 ? N + shift : 0);
+    const int hi = shift > 0 ? (shift < N ? shift : N) : N;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) p[i] = -9999.0f;
 }
 void shift_rows(float *rows, long long nrows, long long row_stride, int N, int shift, cudaStream_t s) {
-    if (nrows <= 0) return;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(shift_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 * 4);
-        configured = true;
-    }
-    shift_rows_kernel<<<(unsigned)nrows, 256, (size_t)N * sizeof(float), s>>>(rows, row_stride, N, shift);
+    if (nrows <= 0 || shift == 0) return;
+    shift_rows_kernel<<<(unsigned)nrows, 256, 0, s>>>(rows, row_stride, N, shift);
 }
 
 }  // namespace rfa
