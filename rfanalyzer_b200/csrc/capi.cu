@@ -319,7 +319,7 @@ static int fft_generic(rfa_ctx *c, int in_kind, int out_kind, const float *in_a,
     L.p.row_stride = out_kind == OUT_CPLX ? 2LL * n : n;
     L.p.nframes = batch;
     L.p.store_from = 0;
-    L.p.inv_n2 = 1.0f / ((float)n * (float)n);
+    L.p.inv_n2 = -3.0102999566398120f * log2f((float)n);  // dB bias, see logmag_db
     cudaError_t e = spectrum_launch(L);
     if (e != cudaSuccess) return cuda_fail(e, "spectrum kernel");
     c->launches++;
@@ -387,7 +387,7 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
     L.p.row_stride = row_stride;
     L.p.nframes = nframes;
     L.p.store_from = store_from;
-    L.p.inv_n2 = 1.0f / ((float)n * (float)n);
+    L.p.inv_n2 = -3.0102999566398120f * log2f((float)n);  // dB bias, see logmag_db
     L.p.peaks = peaks;
     L.p.avg = aq.avg;
     L.p.avg_newest = row0 + (nframes - 1) * row_step;

@@ -91,30 +91,55 @@ struct Dft<8> {
     static RFA_CX int perm(int c) { return 2 * (c & 3) + (c >> 2); }
 };
 
+// radix-4 butterfly whose input a2 is h*s2 (the scaling rides on the adds as FMAs)
+RFA_HD void bfly4_h2(cf &a0, cf &a1, cf s2, cf &a3, cf &o2, float h) {
+    cf t0 = cf{fmaf(h, s2.x, a0.x), fmaf(h, s2.y, a0.y)};
+    cf t1 = cf{fmaf(-h, s2.x, a0.x), fmaf(-h, s2.y, a0.y)};
+    cf t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    o2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+// radix-4 butterfly whose inputs a1, a3 are h*s1, h*s3
+RFA_HD void bfly4_h13(cf &a0, cf s1, cf &a2, cf s3, cf &o1, cf &o3, float h) {
+    cf t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    cf p = cadd(s1, s3), q = mul_mj(csub(s1, s3));
+    a0 = cf{fmaf(h, p.x, t0.x), fmaf(h, p.y, t0.y)};
+    o1 = cf{fmaf(h, q.x, t1.x), fmaf(h, q.y, t1.y)};
+    a2 = cf{fmaf(-h, p.x, t0.x), fmaf(-h, p.y, t0.y)};
+    o3 = cf{fmaf(-h, q.x, t1.x), fmaf(-h, q.y, t1.y)};
+}
+
 template <>
 struct Dft<16> {
     // 4x4 Cooley-Tukey: n = n2 + 4*n1, k = k1 + 4*k2.
     // stage 1: DFT4 over n1 for each n2 -> u[n2 + 4*k1]; twiddle W16^(n2*k1);
     // stage 2: DFT4 over n2 for each k1 -> X[k1 + 4*k2] in u[4*k1 + k2].
+    // The four W16^2 / W16^6 twiddles are h*(1-j) / h*(-1-j): the (1-j), (-1-j) parts cost two adds,
+    // the factor h = 1/sqrt(2) is folded into the stage-2 additions as FMAs.
     static RFA_HD void run(cf *u) {
         const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
         const float h = 0.70710678118654752440f;
 #pragma unroll
         for (int n2 = 0; n2 < 4; n2++) bfly4(u[n2], u[n2 + 4], u[n2 + 8], u[n2 + 12]);
+        // k1 = 0
+        bfly4(u[0], u[1], u[2], u[3]);
         // k1 = 1: W16^1, W16^2, W16^3
         u[5] = cmul(u[5], cf{c1, -s1});
-        u[6] = cf{h * (u[6].x + u[6].y), h * (u[6].y - u[6].x)};
+        const cf s6 = cf{u[6].x + u[6].y, u[6].y - u[6].x};  // u6*(1-j)
         u[7] = cmul(u[7], cf{s1, -c1});
+        bfly4_h2(u[4], u[5], s6, u[7], u[6], h);
         // k1 = 2: W16^2, W16^4, W16^6
-        u[9] = cf{h * (u[9].x + u[9].y), h * (u[9].y - u[9].x)};
+        const cf s9 = cf{u[9].x + u[9].y, u[9].y - u[9].x};      // u9*(1-j)
         u[10] = mul_mj(u[10]);
-        u[11] = cf{h * (u[11].y - u[11].x), -h * (u[11].x + u[11].y)};
+        const cf s11 = cf{u[11].y - u[11].x, -(u[11].x + u[11].y)};  // u11*(-1-j)
+        bfly4_h13(u[8], s9, u[10], s11, u[9], u[11], h);
         // k1 = 3: W16^3, W16^6, W16^9
         u[13] = cmul(u[13], cf{s1, -c1});
-        u[14] = cf{h * (u[14].y - u[14].x), -h * (u[14].x + u[14].y)};
+        const cf s14 = cf{u[14].y - u[14].x, -(u[14].x + u[14].y)};  // u14*(-1-j)
         u[15] = cmul(u[15], cf{-c1, s1});
-#pragma unroll
-        for (int k1 = 0; k1 < 4; k1++) bfly4(u[4 * k1], u[4 * k1 + 1], u[4 * k1 + 2], u[4 * k1 + 3]);
+        bfly4_h2(u[12], u[13], s14, u[15], u[14], h);
     }
     static RFA_CX int perm(int c) { return 4 * (c & 3) + (c >> 2); }
 };
@@ -277,14 +302,16 @@ RFA_HD float magic_half0(uint32_t raw) { return bits_to_float(byte_perm(raw, 0x4
 RFA_HD float magic_half1(uint32_t raw) { return bits_to_float(byte_perm(raw, 0x4B000000u, 0x7632u)); }
 
 // dB scaling of nativedsp.cpp:72-79: 10*log10(sqrt((re/N)^2+(im/N)^2)) = 5*log10(|X|^2/N^2)
-RFA_HD float logmag_db(cf v, float inv_n2) {
-    float pw = fmaf(v.x, v.x, v.y * v.y) * inv_n2;
+//   = 1.50515*log2(|X|^2) - 3.0103*log2(N).  N is a power of two, so the bias is an exact
+// multiple of 3.0103 and the division by N^2 never has to be executed.
+RFA_HD float logmag_db(cf v, float db_bias) {
+    const float pw = fmaf(v.x, v.x, v.y * v.y);
 #ifdef __CUDA_ARCH__
-    float lg;  // MUFU.LG2 without the denormal pre-scaling: |X|^2/N^2 is far from 1e-38, 0 -> -inf
+    float lg;  // MUFU.LG2 without the denormal pre-scaling: 0 -> -inf like log10f(0)
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(pw));
-    return 1.5051499783199060f * lg;
+    return fmaf(1.5051499783199060f, lg, db_bias);
 #else
-    return 1.5051499783199060f * log2f(pw);
+    return fmaf(1.5051499783199060f, log2f(pw), db_bias);
 #endif
 }
 

@@ -50,7 +50,7 @@ struct SpectrumParams {
     long long avg_valid;  // rows that hold data; older terms count as -9999f
     int avg_len;          // L
     unsigned int *ticket; // [8] zeroed counters: [c] finished tail rows, [4+c] CTAs done averaging (residue c < 4)
-    float inv_n2;         // 1/N^2
+    float inv_n2;         // dB bias -3.0103*log2(N) (the 1/N^2 scaling, applied after the logarithm)
 };
 
 template <int NL>

@@ -44,7 +44,7 @@ int emu_one(SpectrumParams p, float *peaks) {
     make_twiddles(N, twN.data());
     p.tw = tw.data();
     p.twN = twN.data();
-    p.inv_n2 = 1.0f / ((float)N * (float)N);
+    p.inv_n2 = -3.0102999566398120f * log2f((float)N);  // dB bias, see logmag_db
     std::vector<cf> x(Plan<NL>::SMEM_POINTS);
     std::vector<std::array<cf, E>> U(T);
     std::vector<std::array<float, E>> PK((size_t)T * S);
