@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "librfa_b200.so")
+# RFA_B200_LIB: load a tuning variant of the same library (kernel experiments); never a fallback
+LIB_PATH = os.environ.get("RFA_B200_LIB") or os.path.join(HERE, "lib", "librfa_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = range(5)
 MEM_HOST, MEM_DEVICE = 0, 1

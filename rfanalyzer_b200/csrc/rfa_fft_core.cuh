@@ -29,12 +29,88 @@ struct cf {
     float x, y;
 };
 
-RFA_HD cf cadd(cf a, cf b) { return cf{a.x + b.x, a.y + b.y}; }
-RFA_HD cf csub(cf a, cf b) { return cf{a.x - b.x, a.y - b.y}; }
+// Packed FP32 (sm_100a): FADD2 / FMUL2 / FFMA2 operate on an aligned register pair, i.e. on one
+// complex value, in ONE issue slot (two FP32-pipe cycles).  SASS operand modifiers give the rest of
+// complex arithmetic for free: .LO_HI swaps the halves, .NP/.PN negate one half (multiplication by
+// -j / +j) and R.F32 broadcasts a scalar, so a complex add is one instruction and a complex multiply
+// two.  ptxas folds the mov.b64 / neg.f32 below into those modifiers (checked with cuobjdump).
+// The kernel is issue-bound (profiles/r01_*), so halving the FP32 issue slots is the point;
+// tools/ubench/fp32x2.cu measures 0.50 FADD2/clk/SMSP vs 0.98 FADD/clk/SMSP on B200.
+#if defined(__CUDA_ARCH__) && !defined(RFA_NO_PACKED)
+#define RFA_PACKED 1
+typedef unsigned long long rfa_u64;
+__device__ __forceinline__ rfa_u64 cpk(float x, float y) {
+    rfa_u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+#endif
+
+#ifdef RFA_PACKED
+__device__ __forceinline__ cf cunpk(rfa_u64 v) {
+    cf a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ cf add2(rfa_u64 a, rfa_u64 b) {
+    rfa_u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return cunpk(r);
+}
+__device__ __forceinline__ cf mul2(rfa_u64 a, rfa_u64 b) {
+    rfa_u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return cunpk(r);
+}
+__device__ __forceinline__ cf fma2(rfa_u64 a, rfa_u64 b, rfa_u64 c) {
+    rfa_u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return cunpk(r);
+}
+#define RFA_PK(v) cpk((v).x, (v).y)
+#endif
+
+RFA_HD cf cadd(cf a, cf b) {
+#ifdef RFA_PACKED
+    return add2(RFA_PK(a), RFA_PK(b));
+#else
+    return cf{a.x + b.x, a.y + b.y};
+#endif
+}
+RFA_HD cf csub(cf a, cf b) {
+#ifdef RFA_PACKED
+    return add2(RFA_PK(a), cpk(-b.x, -b.y));
+#else
+    return cf{a.x - b.x, a.y - b.y};
+#endif
+}
 RFA_HD cf cmul(cf a, cf b) {
+#ifdef RFA_EXP_NOBFLY
+    return a;
+#endif
+#ifdef RFA_PACKED
+    return fma2(cpk(-a.y, a.x), cpk(b.y, b.y), RFA_PK(mul2(RFA_PK(a), cpk(b.x, b.x))));
+#else
     return cf{fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)};
+#endif
 }
 RFA_HD cf mul_mj(cf a) { return cf{a.y, -a.x}; }  // a * (-j)
+// a + h*b, a - h*b with a real scalar h (one FFMA2 each)
+RFA_HD cf caxpy(float h, cf b, cf a) {
+#ifdef RFA_PACKED
+    return fma2(RFA_PK(b), cpk(h, h), RFA_PK(a));
+#else
+    return cf{fmaf(h, b.x, a.x), fmaf(h, b.y, a.y)};
+#endif
+}
+// a * s with a real scalar s
+RFA_HD cf cscale(cf a, float s) {
+#ifdef RFA_PACKED
+    return mul2(RFA_PK(a), cpk(s, s));
+#else
+    return cf{a.x * s, a.y * s};
+#endif
+}
 
 RFA_CX int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
 
@@ -75,9 +151,9 @@ struct Dft<8> {
         const float h = 0.70710678118654752440f;
         bfly4(u[0], u[2], u[4], u[6]);
         bfly4(u[1], u[3], u[5], u[7]);
-        cf o1 = cf{h * (u[3].x + u[3].y), h * (u[3].y - u[3].x)};   // * W8^1
+        cf o1 = cscale(cadd(u[3], mul_mj(u[3])), h);   // * W8^1
         cf o2 = mul_mj(u[5]);                                       // * W8^2
-        cf o3 = cf{h * (u[7].y - u[7].x), -h * (u[7].x + u[7].y)};  // * W8^3
+        cf o3 = cscale(csub(mul_mj(u[7]), u[7]), h);  // * W8^3
         cf e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6], o0 = u[1];
         u[0] = cadd(e0, o0);
         u[1] = csub(e0, o0);
@@ -93,8 +169,8 @@ struct Dft<8> {
 
 // radix-4 butterfly whose input a2 is h*s2 (the scaling rides on the adds as FMAs)
 RFA_HD void bfly4_h2(cf &a0, cf &a1, cf s2, cf &a3, cf &o2, float h) {
-    cf t0 = cf{fmaf(h, s2.x, a0.x), fmaf(h, s2.y, a0.y)};
-    cf t1 = cf{fmaf(-h, s2.x, a0.x), fmaf(-h, s2.y, a0.y)};
+    cf t0 = caxpy(h, s2, a0);
+    cf t1 = caxpy(-h, s2, a0);
     cf t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
     a0 = cadd(t0, t2);
     a1 = cadd(t1, t3);
@@ -105,12 +181,14 @@ RFA_HD void bfly4_h2(cf &a0, cf &a1, cf s2, cf &a3, cf &o2, float h) {
 RFA_HD void bfly4_h13(cf &a0, cf s1, cf &a2, cf s3, cf &o1, cf &o3, float h) {
     cf t0 = cadd(a0, a2), t1 = csub(a0, a2);
     cf p = cadd(s1, s3), q = mul_mj(csub(s1, s3));
-    a0 = cf{fmaf(h, p.x, t0.x), fmaf(h, p.y, t0.y)};
-    o1 = cf{fmaf(h, q.x, t1.x), fmaf(h, q.y, t1.y)};
-    a2 = cf{fmaf(-h, p.x, t0.x), fmaf(-h, p.y, t0.y)};
-    o3 = cf{fmaf(-h, q.x, t1.x), fmaf(-h, q.y, t1.y)};
+    a0 = caxpy(h, p, t0);
+    o1 = caxpy(h, q, t1);
+    a2 = caxpy(-h, p, t0);
+    o3 = caxpy(-h, q, t1);
 }
 
+// Timing experiments only (results are wrong): RFA_EXP_NOBFLY drops the butterflies and twiddle
+// products, RFA_EXP_NOXCHG drops the shared-memory exchanges and barriers.
 template <>
 struct Dft<16> {
     // 4x4 Cooley-Tukey: n = n2 + 4*n1, k = k1 + 4*k2.
@@ -119,6 +197,9 @@ struct Dft<16> {
     // The four W16^2 / W16^6 twiddles are h*(1-j) / h*(-1-j): the (1-j), (-1-j) parts cost two adds,
     // the factor h = 1/sqrt(2) is folded into the stage-2 additions as FMAs.
     static RFA_HD void run(cf *u) {
+#ifdef RFA_EXP_NOBFLY
+        return;
+#endif
         const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
         const float h = 0.70710678118654752440f;
 #pragma unroll
@@ -127,17 +208,17 @@ struct Dft<16> {
         bfly4(u[0], u[1], u[2], u[3]);
         // k1 = 1: W16^1, W16^2, W16^3
         u[5] = cmul(u[5], cf{c1, -s1});
-        const cf s6 = cf{u[6].x + u[6].y, u[6].y - u[6].x};  // u6*(1-j)
+        const cf s6 = cadd(u[6], mul_mj(u[6]));  // u6*(1-j)
         u[7] = cmul(u[7], cf{s1, -c1});
         bfly4_h2(u[4], u[5], s6, u[7], u[6], h);
         // k1 = 2: W16^2, W16^4, W16^6
-        const cf s9 = cf{u[9].x + u[9].y, u[9].y - u[9].x};      // u9*(1-j)
+        const cf s9 = cadd(u[9], mul_mj(u[9]));      // u9*(1-j)
         u[10] = mul_mj(u[10]);
-        const cf s11 = cf{u[11].y - u[11].x, -(u[11].x + u[11].y)};  // u11*(-1-j)
+        const cf s11 = csub(mul_mj(u[11]), u[11]);  // u11*(-1-j)
         bfly4_h13(u[8], s9, u[10], s11, u[9], u[11], h);
         // k1 = 3: W16^3, W16^6, W16^9
         u[13] = cmul(u[13], cf{s1, -c1});
-        const cf s14 = cf{u[14].y - u[14].x, -(u[14].x + u[14].y)};  // u14*(-1-j)
+        const cf s14 = csub(mul_mj(u[14]), u[14]);  // u14*(-1-j)
         u[15] = cmul(u[15], cf{-c1, s1});
         bfly4_h2(u[12], u[13], s14, u[15], u[14], h);
     }
@@ -197,7 +278,11 @@ RFA_HD void pass_gather(const cf *x, const cf *tw, int tid, cf *u) {
             const cf *xi = x + phys(i);
 #pragma unroll
             for (int r = 0; r < R; r++) {
+#ifdef RFA_EXP_NOXCHG
+                cf v = u[b * R + r];
+#else
                 cf v = xi[r * (STR + STR / 16)];
+#endif
                 if (P > 1 && r > 0) v = cmul(v, twk[(r - 1) * P]);
                 u[b * R + r] = v;
             }

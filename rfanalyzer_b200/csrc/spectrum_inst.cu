@@ -1,5 +1,7 @@
 // spectrum_inst.cu -- instantiations of the fused spectrum kernel, compiled once per
 // size group (-DRFA_GROUP=0..3) so the groups build in parallel.
+#include <stdlib.h>
+
 #include "spectrum_launch.h"
 
 namespace rfa {
@@ -25,6 +27,11 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     if (occ < 1) occ = 1;
     long long need = ((L.p.nframes + G::FPC - 1) / G::FPC) * S;
     long long cap = (long long)L.num_sms * occ;
+    static const int maxgrid_env = [] {  // tuning runs only
+        const char *e = getenv("RFA_MAXGRID");
+        return e ? atoi(e) : 0;
+    }();
+    if (maxgrid_env > 0 && maxgrid_env < cap) cap = maxgrid_env;
     if (L.max_grid > 0 && L.max_grid < cap) cap = L.max_grid;
     cap -= cap % S;
     if (cap < S) cap = S;

@@ -82,20 +82,19 @@ RFA_CX float unit_scale() {
 // integer code pair in a register -> (I, Q) * ws
 template <int IN>
 RFA_HD cf decode_point(uint32_t raw, float ws) {
-    cf v;
+    cf m;
     if (IN == FMT_S8) {
         raw ^= 0x8080u;  // two's complement -> offset binary: code + 128
-        v.x = (magic_byte0(raw) - 8388736.0f) * ws;
-        v.y = (magic_byte1(raw) - 8388736.0f) * ws;
+        m = cf{magic_byte0(raw), magic_byte1(raw)};
+        return cscale(cadd(m, cf{-8388736.0f, -8388736.0f}), ws);
     } else if (IN == FMT_U8) {
-        v.x = ((magic_byte0(raw) - 8388608.0f) - 127.4f) * ws;
-        v.y = ((magic_byte1(raw) - 8388608.0f) - 127.4f) * ws;
+        m = cf{magic_byte0(raw), magic_byte1(raw)};
+        return cscale(cadd(cadd(m, cf{-8388608.0f, -8388608.0f}), cf{-127.4f, -127.4f}), ws);
     } else {
         raw ^= 0x80008000u;
-        v.x = (magic_half0(raw) - 8421376.0f) * ws;
-        v.y = (magic_half1(raw) - 8421376.0f) * ws;
+        m = cf{magic_half0(raw), magic_half1(raw)};
+        return cscale(cadd(m, cf{-8421376.0f, -8421376.0f}), ws);
     }
-    return v;
 }
 
 template <int IN>
@@ -106,9 +105,7 @@ RFA_HD cf load_point(const void *in, const float *in_im, long long idx, float ws
     } else if (IN == FMT_S16LE) {
         v = decode_point<IN>(((const uint32_t *)in)[idx], ws);
     } else if (IN == FMT_CF32) {
-        v = ((const cf *)in)[idx];
-        v.x *= ws;
-        v.y *= ws;
+        v = cscale(((const cf *)in)[idx], ws);
     } else {
         v.x = ((const float *)in)[idx] * ws;
         v.y = in_im[idx] * ws;
@@ -149,6 +146,10 @@ struct SpectrumFrame {
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int off = b * T + r * STR;
+#ifdef RFA_EXP_NOLOAD
+                raw[b * R + r] = (uint32_t)(size_t)src + off;
+                continue;
+#endif
                 raw[b * R + r] = (IN == FMT_S16LE) ? ((const uint32_t *)src)[off] : (uint32_t)((const uint16_t *)src)[off];
             }
     }
@@ -217,7 +218,11 @@ struct SpectrumFrame {
             const cf *xi = x + phys(tid + b * T);
 #pragma unroll
             for (int r = 0; r < R; r++) {
+#ifdef RFA_EXP_NOXCHG
+                cf v = u[b * R + r];
+#else
                 cf v = xi[r * (STR + STR / 16)];
+#endif
                 if (r > 0) v = cmul(v, twreg[b * (R - 1) + r - 1]);
                 u[b * R + r] = v;
             }
@@ -242,6 +247,10 @@ struct SpectrumFrame {
                 float *o = out + (c + S * (tid + b * T));
 #pragma unroll
                 for (int cc = 0; cc < R; cc++) {
+#ifdef RFA_EXP_NOEMIT
+                    pk[b * R + cc] = fmaxf(pk[b * R + cc], u[b * R + Dft<R>::perm(cc)].x);
+                    continue;
+#endif
                     const float db = logmag_db(u[b * R + Dft<R>::perm(cc)], inv_n2);
                     if (STORE) o[shifted_offset(S * cc * P)] = db;
                     if (PEAK) pk[b * R + cc] = fmaxf(pk[b * R + cc], db);
@@ -312,8 +321,10 @@ struct MiddlePasses {
         using F = SpectrumFrame<NL, S, IN, OUT>;
         if constexpr (PASS < Plan<NL>::PASSES) {
             cf *x = ((PASS - 1) & 1) ? x1 : x0;
+#ifndef RFA_EXP_NOXCHG
             F::template scatter<PASS - 1>(x, tid, u);
             __syncthreads();
+#endif
             if constexpr (PASS == F::LAST && F::LAST_TW_REG)
                 F::gather_last_reg(x, twreg, tid, u);
             else if constexpr (PASS == F::LAST)
@@ -332,8 +343,13 @@ struct MiddlePasses {
 // The newest avg_len+1 frames ("tail") are therefore finished a few microseconds into the
 // launch; every CTA averages a slice of the bins once it has run out of frames.
 // All per-frame addresses advance by constants, so the loop carries two pointers and a counter.
+// Timing experiments (tools/): RFA_MINCTAS changes the occupancy target, the
+// RFA_EXP_* switches drop one part of the kernel (results are then wrong).
+#ifndef RFA_MINCTAS
+#define RFA_MINCTAS 2
+#endif
 template <int NL, int S, int IN, int OUT>
-__global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? 2 : 1) spectrum_kernel(const SpectrumParams p) {
+__global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINCTAS : 1) spectrum_kernel(const SpectrumParams p) {
     using G = Geom<NL>;
     using F = SpectrumFrame<NL, S, IN, OUT>;
     constexpr int T = G::T, E = G::E, FPC = G::FPC, N = NL * S;

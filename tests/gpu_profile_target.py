@@ -15,7 +15,9 @@ with torch.cuda.stream(stream):
     iqs = [iq.clone() for _ in range(4)]
     rows = [torch.empty((F, N), dtype=torch.float32, device="cuda") for _ in range(4)]
     peaks = torch.zeros(N, dtype=torch.float32, device="cuda"); avg = torch.zeros(N, dtype=torch.float32, device="cuda")
+    var = os.environ.get("VARIANT", "rows+peaks+avg")
     for i in range(8):
-        plan.process(iqs[i % 4], F, rows=rows[i % 4], peaks=peaks, avg=avg, peaks_accumulate=i > 0)
+        plan.process(iqs[i % 4], F, rows=rows[i % 4] if "rows" in var else None, peaks=peaks if "peaks" in var else None,
+                     avg=avg if "avg" in var else None, peaks_accumulate=i > 0)
     stream.synchronize()
 print("done")
