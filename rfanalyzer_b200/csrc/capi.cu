@@ -320,6 +320,12 @@ static int fft_generic(rfa_ctx *c, int in_kind, int out_kind, const float *in_a,
     L.p.nframes = batch;
     L.p.store_from = 0;
     L.p.inv_n2 = -3.0102999566398120f * log2f((float)n);  // dB bias, see logmag_db
+    // chunk counters of the kernel's work distribution (stage[7] is reserved for them)
+    if (!c->stage[7].p) {
+        if (int rc = c->stage[7].ensure(TICKET_WORDS * sizeof(unsigned int))) return rc;
+        RFA_CK(cudaMemsetAsync(c->stage[7].p, 0, TICKET_WORDS * sizeof(unsigned int), c->stream));
+    }
+    L.p.ticket = c->stage[7].as<unsigned int>();
     cudaError_t e = spectrum_launch(L);
     if (e != cudaSuccess) return cuda_fail(e, "spectrum kernel");
     c->launches++;
@@ -424,8 +430,8 @@ int rfa_spectrum_plan_create(rfa_ctx *c, const rfa_spectrum_desc *d, rfa_spectru
     int rc = c->get_twiddles(nl, &pl->tw);
     if (!rc && n > 16384) rc = c->get_twiddles(-n, &pl->twN);
     if (!rc) rc = c->get_window(d->window, n, &pl->win);
-    if (!rc) rc = pl->ticket.ensure(8 * sizeof(unsigned int));
-    if (!rc && cudaMemsetAsync(pl->ticket.p, 0, 8 * sizeof(unsigned int), c->stream) != cudaSuccess) rc = RFA_ERR_CUDA;
+    if (!rc) rc = pl->ticket.ensure(TICKET_WORDS * sizeof(unsigned int));
+    if (!rc && cudaMemsetAsync(pl->ticket.p, 0, TICKET_WORDS * sizeof(unsigned int), c->stream) != cudaSuccess) rc = RFA_ERR_CUDA;
     if (rc) {
         delete pl;
         return rc;

@@ -112,13 +112,73 @@ RFA_HD cf cscale(cf a, float s) {
 #endif
 }
 
+
+// ---------------------------------------------------------------------------
+// c2: the same point of TWO frames (A, B), stored as re(A), re(B), im(A), im(B).  With this
+// layout every real operation of the transform is one packed instruction over both frames, the
+// twiddle / window scalars are shared (R.F32 broadcast) and multiplication by -j is a register
+// renaming.  The dual-frame kernel (spectrum2_kernel.cuh) keeps 16 such values per thread.
+// ---------------------------------------------------------------------------
+struct alignas(16) c2 {
+    float rA, rB, iA, iB;
+};
+
+RFA_HD c2 cadd(c2 a, c2 b) {
+#ifdef RFA_PACKED
+    const cf r = add2(cpk(a.rA, a.rB), cpk(b.rA, b.rB)), i = add2(cpk(a.iA, a.iB), cpk(b.iA, b.iB));
+    return c2{r.x, r.y, i.x, i.y};
+#else
+    return c2{a.rA + b.rA, a.rB + b.rB, a.iA + b.iA, a.iB + b.iB};
+#endif
+}
+RFA_HD c2 csub(c2 a, c2 b) {
+#ifdef RFA_PACKED
+    const cf r = add2(cpk(a.rA, a.rB), cpk(-b.rA, -b.rB)), i = add2(cpk(a.iA, a.iB), cpk(-b.iA, -b.iB));
+    return c2{r.x, r.y, i.x, i.y};
+#else
+    return c2{a.rA - b.rA, a.rB - b.rB, a.iA - b.iA, a.iB - b.iB};
+#endif
+}
+RFA_HD c2 mul_mj(c2 a) { return c2{a.iA, a.iB, -a.rA, -a.rB}; }
+RFA_HD c2 cmul(c2 a, cf w) {
+#ifdef RFA_EXP_NOBFLY
+    return a;
+#endif
+#ifdef RFA_PACKED
+    const rfa_u64 re = cpk(a.rA, a.rB), im = cpk(a.iA, a.iB), wr = cpk(w.x, w.x), wi = cpk(w.y, w.y);
+    const cf t = mul2(im, wi), s = mul2(re, wi);
+    const cf r = fma2(re, wr, cpk(-t.x, -t.y)), i = fma2(im, wr, RFA_PK(s));
+    return c2{r.x, r.y, i.x, i.y};
+#else
+    return c2{fmaf(a.rA, w.x, -(a.iA * w.y)), fmaf(a.rB, w.x, -(a.iB * w.y)), fmaf(a.iA, w.x, a.rA * w.y),
+              fmaf(a.iB, w.x, a.rB * w.y)};
+#endif
+}
+RFA_HD c2 caxpy(float h, c2 b, c2 a) {
+#ifdef RFA_PACKED
+    const cf r = fma2(cpk(b.rA, b.rB), cpk(h, h), cpk(a.rA, a.rB)), i = fma2(cpk(b.iA, b.iB), cpk(h, h), cpk(a.iA, a.iB));
+    return c2{r.x, r.y, i.x, i.y};
+#else
+    return c2{fmaf(h, b.rA, a.rA), fmaf(h, b.rB, a.rB), fmaf(h, b.iA, a.iA), fmaf(h, b.iB, a.iB)};
+#endif
+}
+RFA_HD c2 cscale(c2 a, float s) {
+#ifdef RFA_PACKED
+    const cf r = mul2(cpk(a.rA, a.rB), cpk(s, s)), i = mul2(cpk(a.iA, a.iB), cpk(s, s));
+    return c2{r.x, r.y, i.x, i.y};
+#else
+    return c2{a.rA * s, a.rB * s, a.iA * s, a.iB * s};
+#endif
+}
+
 RFA_CX int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
 
 // ---------------------------------------------------------------------------
 // In-register DFTs.  dftR(u) leaves natural-order output c in u[perm<R>(c)].
 // ---------------------------------------------------------------------------
-RFA_HD void bfly4(cf &a0, cf &a1, cf &a2, cf &a3) {
-    cf t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
+template <class V>
+RFA_HD void bfly4(V &a0, V &a1, V &a2, V &a3) {
+    V t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
     a0 = cadd(t0, t2);
     a1 = cadd(t1, t3);
     a2 = csub(t0, t2);
@@ -130,8 +190,9 @@ struct Dft;
 
 template <>
 struct Dft<2> {
-    static RFA_HD void run(cf *u) {
-        cf t = u[0];
+    template <class V>
+    static RFA_HD void run(V *u) {
+        V t = u[0];
         u[0] = cadd(t, u[1]);
         u[1] = csub(t, u[1]);
     }
@@ -140,21 +201,23 @@ struct Dft<2> {
 
 template <>
 struct Dft<4> {
-    static RFA_HD void run(cf *u) { bfly4(u[0], u[1], u[2], u[3]); }
+    template <class V>
+    static RFA_HD void run(V *u) { bfly4(u[0], u[1], u[2], u[3]); }
     static RFA_CX int perm(int c) { return c; }
 };
 
 template <>
 struct Dft<8> {
     // even part in u[0,2,4,6], odd part in u[1,3,5,7]; X[k] -> u[2k], X[k+4] -> u[2k+1]
-    static RFA_HD void run(cf *u) {
+    template <class V>
+    static RFA_HD void run(V *u) {
         const float h = 0.70710678118654752440f;
         bfly4(u[0], u[2], u[4], u[6]);
         bfly4(u[1], u[3], u[5], u[7]);
-        cf o1 = cscale(cadd(u[3], mul_mj(u[3])), h);   // * W8^1
-        cf o2 = mul_mj(u[5]);                                       // * W8^2
-        cf o3 = cscale(csub(mul_mj(u[7]), u[7]), h);  // * W8^3
-        cf e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6], o0 = u[1];
+        V o1 = cscale(cadd(u[3], mul_mj(u[3])), h);   // * W8^1
+        V o2 = mul_mj(u[5]);                          // * W8^2
+        V o3 = cscale(csub(mul_mj(u[7]), u[7]), h);   // * W8^3
+        V e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6], o0 = u[1];
         u[0] = cadd(e0, o0);
         u[1] = csub(e0, o0);
         u[2] = cadd(e1, o1);
@@ -168,19 +231,21 @@ struct Dft<8> {
 };
 
 // radix-4 butterfly whose input a2 is h*s2 (the scaling rides on the adds as FMAs)
-RFA_HD void bfly4_h2(cf &a0, cf &a1, cf s2, cf &a3, cf &o2, float h) {
-    cf t0 = caxpy(h, s2, a0);
-    cf t1 = caxpy(-h, s2, a0);
-    cf t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
+template <class V>
+RFA_HD void bfly4_h2(V &a0, V &a1, V s2, V &a3, V &o2, float h) {
+    V t0 = caxpy(h, s2, a0);
+    V t1 = caxpy(-h, s2, a0);
+    V t2 = cadd(a1, a3), t3 = mul_mj(csub(a1, a3));
     a0 = cadd(t0, t2);
     a1 = cadd(t1, t3);
     o2 = csub(t0, t2);
     a3 = csub(t1, t3);
 }
 // radix-4 butterfly whose inputs a1, a3 are h*s1, h*s3
-RFA_HD void bfly4_h13(cf &a0, cf s1, cf &a2, cf s3, cf &o1, cf &o3, float h) {
-    cf t0 = cadd(a0, a2), t1 = csub(a0, a2);
-    cf p = cadd(s1, s3), q = mul_mj(csub(s1, s3));
+template <class V>
+RFA_HD void bfly4_h13(V &a0, V s1, V &a2, V s3, V &o1, V &o3, float h) {
+    V t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    V p = cadd(s1, s3), q = mul_mj(csub(s1, s3));
     a0 = caxpy(h, p, t0);
     o1 = caxpy(h, q, t1);
     a2 = caxpy(-h, p, t0);
@@ -196,7 +261,8 @@ struct Dft<16> {
     // stage 2: DFT4 over n2 for each k1 -> X[k1 + 4*k2] in u[4*k1 + k2].
     // The four W16^2 / W16^6 twiddles are h*(1-j) / h*(-1-j): the (1-j), (-1-j) parts cost two adds,
     // the factor h = 1/sqrt(2) is folded into the stage-2 additions as FMAs.
-    static RFA_HD void run(cf *u) {
+    template <class V>
+    static RFA_HD void run(V *u) {
 #ifdef RFA_EXP_NOBFLY
         return;
 #endif
@@ -208,17 +274,17 @@ struct Dft<16> {
         bfly4(u[0], u[1], u[2], u[3]);
         // k1 = 1: W16^1, W16^2, W16^3
         u[5] = cmul(u[5], cf{c1, -s1});
-        const cf s6 = cadd(u[6], mul_mj(u[6]));  // u6*(1-j)
+        const V s6 = cadd(u[6], mul_mj(u[6]));  // u6*(1-j)
         u[7] = cmul(u[7], cf{s1, -c1});
         bfly4_h2(u[4], u[5], s6, u[7], u[6], h);
         // k1 = 2: W16^2, W16^4, W16^6
-        const cf s9 = cadd(u[9], mul_mj(u[9]));      // u9*(1-j)
+        const V s9 = cadd(u[9], mul_mj(u[9]));      // u9*(1-j)
         u[10] = mul_mj(u[10]);
-        const cf s11 = csub(mul_mj(u[11]), u[11]);  // u11*(-1-j)
+        const V s11 = csub(mul_mj(u[11]), u[11]);  // u11*(-1-j)
         bfly4_h13(u[8], s9, u[10], s11, u[9], u[11], h);
         // k1 = 3: W16^3, W16^6, W16^9
         u[13] = cmul(u[13], cf{s1, -c1});
-        const cf s14 = csub(mul_mj(u[14]), u[14]);  // u14*(-1-j)
+        const V s14 = csub(mul_mj(u[14]), u[14]);  // u14*(-1-j)
         u[15] = cmul(u[15], cf{-c1, s1});
         bfly4_h2(u[12], u[13], s14, u[15], u[14], h);
     }
@@ -263,8 +329,8 @@ RFA_CX int pass_tw_total() {
 // `u` holds E/R butterflies of R points each, butterfly b is i = tid + b*T.
 // All strides are multiples of 16, so phys(i + r*STR) = phys(i) + r*(STR + STR/16): one
 // address per butterfly, the rest are immediate offsets.
-template <int NL, int T, int R, int P>
-RFA_HD void pass_gather(const cf *x, const cf *tw, int tid, cf *u) {
+template <int NL, int T, int R, int P, class V>
+RFA_HD void pass_gather(const V *x, const cf *tw, int tid, V *u) {
     constexpr int E = NL / T;
     constexpr int NB = E / R;
     constexpr int STR = NL / R;
@@ -275,13 +341,13 @@ RFA_HD void pass_gather(const cf *x, const cf *tw, int tid, cf *u) {
         const int k = i & (P - 1);
         const cf *twk = tw + k;
         if (STR % 16 == 0) {
-            const cf *xi = x + phys(i);
+            const V *xi = x + phys(i);
 #pragma unroll
             for (int r = 0; r < R; r++) {
 #ifdef RFA_EXP_NOXCHG
-                cf v = u[b * R + r];
+                V v = u[b * R + r];
 #else
-                cf v = xi[r * (STR + STR / 16)];
+                V v = xi[r * (STR + STR / 16)];
 #endif
                 if (P > 1 && r > 0) v = cmul(v, twk[(r - 1) * P]);
                 u[b * R + r] = v;
@@ -289,7 +355,7 @@ RFA_HD void pass_gather(const cf *x, const cf *tw, int tid, cf *u) {
         } else {
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                cf v = x[phys(i + r * STR)];
+                V v = x[phys(i + r * STR)];
                 if (P > 1 && r > 0) v = cmul(v, twk[(r - 1) * P]);
                 u[b * R + r] = v;
             }
@@ -301,8 +367,8 @@ RFA_HD void pass_gather(const cf *x, const cf *tw, int tid, cf *u) {
 // One pass, scatter side: natural-order output c of butterfly i goes to
 // y[(i-k)*R + k + c*P].  For P a multiple of 16 the c-offsets are immediates; the first
 // pass (P = 1, R = 16) writes 16 consecutive points, phys(16*i + c) = 17*i + c.
-template <int NL, int T, int R, int P>
-RFA_HD void pass_scatter(cf *y, int tid, const cf *u) {
+template <int NL, int T, int R, int P, class V>
+RFA_HD void pass_scatter(V *y, int tid, const V *u) {
     constexpr int E = NL / T;
     constexpr int NB = E / R;
 #pragma unroll
@@ -311,11 +377,11 @@ RFA_HD void pass_scatter(cf *y, int tid, const cf *u) {
         const int k = i & (P - 1);
         const int j = (i - k) * R + k;
         if (P % 16 == 0) {
-            cf *yj = y + phys(j);
+            V *yj = y + phys(j);
 #pragma unroll
             for (int c = 0; c < R; c++) yj[c * (P + P / 16)] = u[b * R + Dft<R>::perm(c)];
         } else if (P == 1 && R == 16) {
-            cf *yj = y + 17 * i;
+            V *yj = y + 17 * i;
 #pragma unroll
             for (int c = 0; c < R; c++) yj[c] = u[b * R + Dft<R>::perm(c)];
         } else {
@@ -326,8 +392,8 @@ RFA_HD void pass_scatter(cf *y, int tid, const cf *u) {
 }
 
 // First pass without the gather: caller filled u[b*R + r] with point (tid + b*T) + r*NL/R.
-template <int NL, int T, int R>
-RFA_HD void pass_first_compute(cf *u) {
+template <int NL, int T, int R, class V>
+RFA_HD void pass_first_compute(V *u) {
     constexpr int NB = (NL / T) / R;
 #pragma unroll
     for (int b = 0; b < NB; b++) Dft<R>::run(u + b * R);

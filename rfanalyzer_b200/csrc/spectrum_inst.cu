@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "spectrum_launch.h"
+#include "spectrum2_kernel.cuh"
 
 namespace rfa {
 namespace {
@@ -33,6 +34,9 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     }();
     if (maxgrid_env > 0 && maxgrid_env < cap) cap = maxgrid_env;
     if (L.max_grid > 0 && L.max_grid < cap) cap = L.max_grid;
+    // the averaging CTA (spectrum_kernel.cuh: average_cta) takes one resident slot
+    const bool avg_cta = OUT == OUT_DB && L.p.avg != nullptr;
+    if (avg_cta && cap > S) cap -= 1;
     cap -= cap % S;
     if (cap < S) cap = S;
     long long grid = need < cap ? need : cap;
@@ -40,12 +44,63 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     if (grid_out) *grid_out = (int)grid;
     if (spc_out) *spc_out = G::FPC;
     if (query) return cudaSuccess;
+    if (avg_cta) grid += 1;
     kern<<<(unsigned)grid, G::CTA, SMEM, L.stream>>>(L.p);
     return cudaGetLastError();
 }
 
+// dual-frame kernel (spectrum2_kernel.cuh): one 256-thread CTA per SM, two frames per thread
+template <int NL, int IN>
+cudaError_t launch_two(const SpectrumLaunch &L, bool query, int *grid_out, int *spc_out) {
+    using G = Geom2<NL>;
+    constexpr size_t SMEM = SpectrumFrame2<NL, IN>::SMEM_BYTES;
+    auto kern = spectrum2_kernel<NL, IN>;
+    static bool configured = false;
+    cudaError_t err;
+    if (!configured) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (err != cudaSuccess) return err;
+        configured = true;
+    }
+    int occ = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::CTA, SMEM);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    const long long npairs = (L.p.nframes + 1) / 2;
+    long long need = (npairs + G::FPC - 1) / G::FPC;
+    long long cap = (long long)L.num_sms * occ;
+    if (L.max_grid > 0 && L.max_grid < cap) cap = L.max_grid;
+    const bool avg_cta = L.p.avg != nullptr;  // the averaging CTA takes one resident slot
+    if (avg_cta && cap > 1) cap -= 1;
+    long long grid = need < cap ? need : cap;
+    if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
+    if (spc_out) *spc_out = 2 * G::FPC;
+    if (query) return cudaSuccess;
+    if (avg_cta) grid += 1;
+    kern<<<(unsigned)grid, G::CTA, SMEM, L.stream>>>(L.p);
+    return cudaGetLastError();
+}
+
+// RFA_DUAL=1 selects the dual-frame kernel for N = 256 .. 4096 (read at every launch so that tests
+// and timing runs can switch).  Default: the single-frame kernel, which is ahead on B200 for now
+// (gpurun_out/timing17.log: 45.5 us vs 47.5 us per 2^24 samples at N = 4096).
+static bool dual_enabled() {
+    const char *e = getenv("RFA_DUAL");
+    return e && atoi(e) == 1;
+}
+
 template <int NL, int S>
 cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc) {
+    if constexpr (S == 1 && NL >= 256 && NL <= 4096) {
+        if (L.out_kind == OUT_DB && dual_enabled()) {
+            switch (L.in_fmt) {
+                case FMT_S8: return launch_two<NL, FMT_S8>(L, query, grid, spc);
+                case FMT_U8: return launch_two<NL, FMT_U8>(L, query, grid, spc);
+                case FMT_S16LE: return launch_two<NL, FMT_S16LE>(L, query, grid, spc);
+            }
+        }
+    }
     if (L.out_kind == OUT_CPLX) {
         if (L.in_fmt == FMT_CF32) return launch_one<NL, S, FMT_CF32, OUT_CPLX>(L, query, grid, spc);
         return cudaErrorInvalidValue;
@@ -102,3 +157,15 @@ cudaError_t spectrum_group3(const SpectrumLaunch &L, bool query, int *grid, int 
 #endif
 
 }  // namespace rfa
+
+#if defined(RFA_TRACE) && RFA_GROUP == 2
+// tuning builds: copy the phase stamps of the last N = 4096 / 8192 launch to the host
+extern "C" int rfa_debug_trace(long long *out, int ctas, int slots) {
+    static long long host[512][RFA_TRACE_SLOTS];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(host, rfa::g_trace, sizeof(host)) != cudaSuccess) return -2;
+    for (int c = 0; c < ctas && c < 512; c++)
+        for (int k = 0; k < slots && k < RFA_TRACE_SLOTS; k++) out[(size_t)c * slots + k] = host[c][k];
+    return 0;
+}
+#endif

@@ -301,6 +301,21 @@ RFA_HD float boxcar_average(const SpectrumParams &p, int i, LoadFn load) {
 }
 
 #ifdef __CUDACC__
+// RFA_TRACE (tuning builds only): thread 0 of every CTA stamps clock64() at phase boundaries into
+// g_trace[cta][slot]; tools read it back through rfa_debug_trace().
+#ifdef RFA_TRACE
+#define RFA_TRACE_SLOTS 128
+__device__ long long g_trace[512][RFA_TRACE_SLOTS];
+#define RFA_STAMP(k)                                                                          \
+    do {                                                                                      \
+        if (threadIdx.x == 0 && (k) < RFA_TRACE_SLOTS) g_trace[blockIdx.x & 511][(k)] = clock64(); \
+    } while (0)
+#else
+#define RFA_STAMP(k) \
+    do {             \
+    } while (0)
+#endif
+
 // max for floats of either sign through the integer atomics (RED.MAX / RED.MIN)
 __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
     if (v >= 0.0f)
@@ -317,13 +332,15 @@ struct MiddlePasses {
     // tw_mid: tables of the middle passes (shared-memory copy when it fits), tw_all: the
     // complete global table (the last pass reads it when its twiddles are not in registers)
     static __device__ __forceinline__ void run(cf *x0, cf *x1, const cf *tw_mid, const cf *tw_all, const cf *twreg,
-                                               int tid, cf *u) {
+                                               int tid, cf *u, int tbase = 0) {
         using F = SpectrumFrame<NL, S, IN, OUT>;
         if constexpr (PASS < Plan<NL>::PASSES) {
             cf *x = ((PASS - 1) & 1) ? x1 : x0;
 #ifndef RFA_EXP_NOXCHG
             F::template scatter<PASS - 1>(x, tid, u);
+            RFA_STAMP(tbase + 2 * PASS - 1);  // scatter issued
             __syncthreads();
+            RFA_STAMP(tbase + 2 * PASS);      // barrier passed
 #endif
             if constexpr (PASS == F::LAST && F::LAST_TW_REG)
                 F::gather_last_reg(x, twreg, tid, u);
@@ -332,51 +349,119 @@ struct MiddlePasses {
             else
                 F::template gather<PASS>(x, tw_mid, tid, u);
             if constexpr (Geom<NL>::NBUF == 1 && PASS + 1 < Plan<NL>::PASSES) __syncthreads();
-            MiddlePasses<NL, S, IN, OUT, PASS + 1>::run(x0, x1, tw_mid, tw_all, twreg, tid, u);
+            MiddlePasses<NL, S, IN, OUT, PASS + 1>::run(x0, x1, tw_mid, tw_all, twreg, tid, u, tbase);
         }
     }
 };
 
 // Frame schedule.  Work item v (0 .. nframes-1) is frame nframes-1-v: the newest frames are
-// transformed FIRST, by the first groups in their first iteration.  Item v belongs to slot
-// (v mod slots) and is that slot's iteration (v div slots), slots = groups * FPC.
-// The newest avg_len+1 frames ("tail") are therefore finished a few microseconds into the
-// launch; every CTA averages a slice of the bins once it has run out of frames.
-// All per-frame addresses advance by constants, so the loop carries two pointers and a counter.
+// transformed FIRST.  Items are handed out in chunks of FPC consecutive items (one per frame slot
+// of the CTA): every group starts on chunks `group` and `group + groups`, later chunks come from an
+// atomic counter, fetched two iterations ahead so that the raw IQ of the next chunk is in flight
+// while the current one is transformed.  (On B200 the two CTAs of an SM do not run at the same
+// speed -- the scheduler favours one of them -- so a static split leaves the SM half empty at the
+// end: gpurun_out/trace1.log.)
+// The newest avg_len+1 frames ("tail") are finished in the first iteration or two and counted in a
+// ticket; one extra CTA at the end of the grid computes the time average from them (average_cta).
+// ticket[0..3]: finished tail rows per residue, [4]: CTAs done, [8..11]: chunk counters per
+// residue; the last CTA of the launch re-arms them all for the next launch.
 // Timing experiments (tools/): RFA_MINCTAS changes the occupancy target, the
 // RFA_EXP_* switches drop one part of the kernel (results are then wrong).
 #ifndef RFA_MINCTAS
 #define RFA_MINCTAS 2
 #endif
+enum : int { TICKET_TAIL = 0, TICKET_DONE = 4, TICKET_WORK = 8, TICKET_WORDS = 12 };
+
+// AnalyzerSurface.kt:710-714: avg[i] = (sum of the newest L+1 rows, newest -> oldest, float32) / (L+1).
+// Run by the launch's LAST CTA, which does nothing else.  The launcher leaves it one resident slot
+// (workers = capacity - 1), so it sleeps beside the workers until the tail rows are counted, a few
+// microseconds into the launch, averages while they transform, and leaves; the dynamic chunk
+// hand-out makes up for the missing worker.  No worker ever waits, and the transform loop carries
+// none of this code.
+__device__ __forceinline__ float average_row_term(const SpectrumParams &p, int r, long long i) {
+    long long row = p.avg_newest + (long long)r * p.avg_dir;
+    if (p.ring_rows > 0) {
+        row %= p.ring_rows;
+        if (row < 0) row += p.ring_rows;
+    }
+    return __ldcg(p.rows + row * p.row_stride + i);
+}
+__device__ __forceinline__ void average_cta(const SpectrumParams &p, int S, int N, int n_tail) {
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < S; c++) {
+            volatile unsigned int *t = p.ticket + TICKET_TAIL + c;
+            while (*t < (unsigned int)n_tail) __nanosleep(256);
+        }
+    }
+    __syncthreads();
+    __threadfence();  // the workers' rows, published before their counts
+#pragma unroll 1
+    for (int i = (int)threadIdx.x; i < N; i += (int)blockDim.x) {
+        float v[31];
+#pragma unroll
+        for (int r = 0; r < 31; r++) {
+            v[r] = -9999.0f;
+            if (r <= p.avg_len && r < p.avg_valid) v[r] = average_row_term(p, r, i);
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 31; r++)
+            if (r <= p.avg_len) sum = __fadd_rn(sum, v[r]);
+        p.avg[i] = __fdiv_rn(sum, (float)(p.avg_len + 1));
+    }
+}
+
+// every thread of a worker CTA that has just stored `cnt` tail rows of residue c (CTA-uniform)
+__device__ __forceinline__ void publish_tail(const SpectrumParams &p, int c, int cnt) {
+    __threadfence();  // rows of this CTA visible before the count
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.ticket + TICKET_TAIL + c, (unsigned int)cnt);
+}
+
+// the last CTA of the launch to leave re-arms the counters for the next launch
+__device__ __forceinline__ void retire_cta(const SpectrumParams &p) {
+    if (threadIdx.x == 0) {
+        if (atomicAdd(p.ticket + TICKET_DONE, 1u) == gridDim.x - 1u) {
+#pragma unroll
+            for (int k = 0; k < TICKET_WORDS; k++) p.ticket[k] = 0u;
+        }
+    }
+}
+
 template <int NL, int S, int IN, int OUT>
 __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINCTAS : 1) spectrum_kernel(const SpectrumParams p) {
     using G = Geom<NL>;
     using F = SpectrumFrame<NL, S, IN, OUT>;
     constexpr int T = G::T, E = G::E, FPC = G::FPC, N = NL * S;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_chunk[2];
+    RFA_STAMP(0);
+    const bool want_avg = (OUT == OUT_DB) && p.avg != nullptr;
+    const bool want_peak = (OUT == OUT_DB) && p.peaks != nullptr;
+    const int n_tail = want_avg ? (int)(p.nframes < p.avg_len + 1 ? p.nframes : p.avg_len + 1) : 0;
+    const int nworkers = (int)gridDim.x - (want_avg ? 1 : 0);  // the launcher adds the averaging CTA
+    if ((int)blockIdx.x == nworkers) {
+        average_cta(p, S, N, n_tail);
+        retire_cta(p);
+        return;
+    }
     const int sub = threadIdx.x / T, tid = threadIdx.x % T;
     cf *x0 = reinterpret_cast<cf *>(smem_raw) + (size_t)sub * G::NBUF * Plan<NL>::SMEM_POINTS;
     cf *x1 = G::NBUF == 2 ? x0 + Plan<NL>::SMEM_POINTS : x0;
 
     const int c = (S == 1) ? 0 : (int)(blockIdx.x % S);
-    const int groups = gridDim.x / S, group = blockIdx.x / S;
-    const long long slots = (long long)groups * FPC, slot = (long long)group * FPC + sub;
-    // iteration counts (frames per slot fit an int: a slot never sees more than 2^31 frames)
-    const int iters = (int)((p.nframes + slots - 1) / slots);                 // CTA-uniform
-    const int my_iters = slot < p.nframes ? (int)((p.nframes - slot + slots - 1) / slots) : 0;
-    const bool want_avg = (OUT == OUT_DB) && p.avg != nullptr;
-    const bool want_peak = (OUT == OUT_DB) && p.peaks != nullptr;
-    const long long n_tail = want_avg ? (p.nframes < p.avg_len + 1 ? p.nframes : p.avg_len + 1) : 0;
-    // rows of frames >= store_from are written: items v <= nframes-1-store_from
-    int store_iters = my_iters;
-    if (p.store_from > 0) {
-        const long long vmax = p.nframes - 1 - p.store_from;  // may be negative
-        store_iters = vmax >= slot ? (int)((vmax - slot) / slots) + 1 : 0;
+    const int groups = nworkers / S, group = blockIdx.x / S;
+    const int nchunks = (int)((p.nframes + FPC - 1) / FPC);  // < 2^31, checked by the launcher
+    constexpr int BPS = in_elem_bytes<IN>();
+
+    // chunk q -> item v = q*FPC + sub -> frame nframes-1-v
+    int q = group, q_next = group + groups, q_next2 = group + 2 * groups;
+    cf u[E];
+    uint32_t raw[F::PREFETCH ? E : 1];
+    if constexpr (F::PREFETCH) {  // first: get the raw IQ of the first frame moving
+        const long long v = (long long)q * FPC + sub;
+        if (v < p.nframes) F::load_raw((const char *)p.in + ((p.nframes - 1 - v) * (long long)N + tid) * BPS, raw);
     }
-    // iterations in which this CTA finishes tail rows (items group*FPC + it*slots < n_tail)
-    const int tail_iters = (want_avg && (long long)group * FPC < n_tail)
-                               ? (int)((n_tail - (long long)group * FPC + slots - 1) / slots)
-                               : 0;
 
     // middle-pass twiddle tables: one shared-memory copy per CTA
     const cf *tw = p.tw;
@@ -384,7 +469,6 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
         cf *stw = reinterpret_cast<cf *>(smem_raw + G::SMEM);
         for (int i = threadIdx.x; i < F::MID_TW; i += G::CTA) stw[i] = p.tw[i];
         tw = stw;
-        __syncthreads();
     }
     // last-pass twiddles and window taps of this thread never change: registers.
     // The window is pre-multiplied by the format's power-of-two unit.
@@ -402,27 +486,29 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     float pk[E];
 #pragma unroll
     for (int e = 0; e < E; e++) pk[e] = -999999.0f;
-
-    // frame of iteration `it` is f = nframes-1-slot - it*slots: input and (linear) row pointers
-    // step by constants
-    long long f = p.nframes - 1 - slot;
-    const char *src = (const char *)p.in + (f * (long long)N + tid) * in_elem_bytes<IN>();
-    const long long src_step = slots * (long long)N * in_elem_bytes<IN>();
-    float *out = p.rows + (p.ring_rows > 0 ? 0 : (p.row0 + f * p.row_step) * p.row_stride);
-    const long long out_step = slots * p.row_step * p.row_stride;
     const float inv_n2 = p.inv_n2;
+    bool worked = false;
+    unsigned int pending = 0;
+    if (threadIdx.x == 0) pending = atomicAdd(p.ticket + TICKET_WORK + c, 1u);
+    __syncthreads();  // twiddle copy
 
-    cf u[E];
-    uint32_t raw[F::PREFETCH ? E : 1];
-    if constexpr (F::PREFETCH)
-        if (my_iters > 0) F::load_raw(src, raw);
-
-    for (int it = 0; it < iters; it++) {
-        const bool active = it < my_iters;
+    RFA_STAMP(1);  // prologue done (slot 0 is stamped at kernel entry)
+    for (int it = 0; q < nchunks; it++) {  // q is CTA-uniform
+        const long long v = (long long)q * FPC + sub;
+        const bool active = v < p.nframes;
+        const long long f = p.nframes - 1 - v;
+        RFA_STAMP(8 + 8 * it);  // iteration start; +1..+4 exchanges, +6 after the last butterflies, +7 after emit
+        // chunk after next: thread 0 asks now, everybody reads it at the end of the iteration
+        // the chunk for three iterations on: thread 0 posts the counter value it asked for one iteration
+        // ago (long since returned) and asks for the next; everybody reads the post at the end of the iteration
+        if (threadIdx.x == 0) {
+            s_chunk[it & 1] = 3 * groups + (int)pending;
+            pending = atomicAdd(p.ticket + TICKET_WORK + c, 1u);
+        }
         if constexpr (F::PREFETCH) {
             if (active) F::first_from_raw(raw, wreg, u);
-            src -= src_step;
-            if (it + 1 < my_iters) F::load_raw(src, raw);  // lands while this frame is transformed
+            const long long vn = (long long)q_next * FPC + sub;  // lands while this frame is transformed
+            if (vn < p.nframes) F::load_raw((const char *)p.in + ((p.nframes - 1 - vn) * (long long)N + tid) * BPS, raw);
         } else {
             if (active) F::first(p, f, c, tid, wreg, u);
         }
@@ -430,10 +516,15 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
         // scatter; with ping-pong buffers and an even number of exchanges the barriers inside
         // the passes already order it (PASSES-1 exchanges alternate A,B,A,...)
         if (it > 0 && (G::NBUF == 1 || ((Plan<NL>::PASSES - 1) & 1))) __syncthreads();
-        if constexpr (Plan<NL>::PASSES > 1) MiddlePasses<NL, S, IN, OUT, 1>::run(x0, x1, tw, p.tw, twreg, tid, u);
+        if constexpr (Plan<NL>::PASSES > 1)
+            MiddlePasses<NL, S, IN, OUT, 1>::run(x0, x1, tw, p.tw, twreg, tid, u, 8 + 8 * it);
+        else
+            __syncthreads();
+        RFA_STAMP(8 + 8 * it + 6);
         if (active) {
-            if (p.ring_rows > 0) out = p.rows + frame_row(p, f) * p.row_stride;
-            if (it < store_iters) {
+            worked = true;
+            float *out = p.rows + frame_row(p, f) * p.row_stride;
+            if (f >= p.store_from) {
                 if (want_peak)
                     F::template emit<true, true>(out, c, tid, u, pk, inv_n2);
                 else
@@ -442,64 +533,32 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
                 F::template emit<true, false>(out, c, tid, u, pk, inv_n2);
             }
         }
-        f -= slots;
-        out -= out_step;
-        // publish finished tail rows (CTA-uniform test; only the first iteration or two)
-        if (it < tail_iters) {
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const long long v0 = (long long)group * FPC + it * slots;
-                const long long cnt = (n_tail - v0 < FPC) ? n_tail - v0 : FPC;
-                atomicAdd(p.ticket + c, (unsigned int)cnt);
-            }
+        RFA_STAMP(8 + 8 * it + 7);
+        // tail rows of this chunk (CTA-uniform test; only the first iteration or two)
+        if (q < 32 && q * FPC < n_tail) {  // n_tail <= 31
+            const int cnt = (n_tail - q * FPC < FPC) ? n_tail - q * FPC : FPC;
+            publish_tail(p, c, cnt);
         }
+        q = q_next;
+        q_next = q_next2;
+        q_next2 = s_chunk[it & 1];  // written before a barrier of this iteration, rewritten two iterations on
     }
 
-    if (want_peak && my_iters > 0) {
+    RFA_STAMP(2);  // main loop done
+    if (want_peak && worked) {
 #pragma unroll
         for (int e = 0; e < E; e++) atomic_max_float(p.peaks + F::peak_index(c, tid, e), pk[e]);
     }
-
-    // time average (AnalyzerSurface.kt:710-714).  The tail rows were finished long ago by CTAs
-    // that wait on nobody; every CTA takes a slice of its residue's bins, one bin per thread,
-    // all L+1 loads of a bin in flight at once, summed newest -> oldest in float32.
-    if (want_avg) {
-        if (threadIdx.x == 0) {
-            volatile unsigned int *t = p.ticket + c;
-            while (*t < (unsigned int)n_tail) __nanosleep(64);
-        }
-        __syncthreads();
-        __threadfence();
-        for (int i = c + S * (group + groups * (int)threadIdx.x); i < N; i += S * groups * G::CTA) {
-            float v[31];
-#pragma unroll
-            for (int r = 0; r < 31; r++) {
-                v[r] = -9999.0f;
-                if (r <= p.avg_len && r < p.avg_valid) {
-                    long long row = p.avg_newest + (long long)r * p.avg_dir;
-                    if (p.ring_rows > 0) {
-                        row %= p.ring_rows;
-                        if (row < 0) row += p.ring_rows;
-                    }
-                    v[r] = __ldcg(p.rows + row * p.row_stride + i);
-                }
-            }
-            float sum = 0.0f;
-#pragma unroll
-            for (int r = 0; r < 31; r++)
-                if (r <= p.avg_len) sum = __fadd_rn(sum, v[r]);
-            p.avg[i] = __fdiv_rn(sum, (float)(p.avg_len + 1));
-        }
-        // the last CTA of this residue to get here re-arms the counters for the next launch
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (atomicAdd(p.ticket + 4 + c, 1u) == (unsigned int)groups - 1u) {
-                p.ticket[c] = 0u;
-                p.ticket[4 + c] = 0u;
-            }
-        }
+    RFA_STAMP(3);  // peak atomics issued
+    retire_cta(p);
+    RFA_STAMP(4);  // kernel end
+#ifdef RFA_TRACE
+    if (threadIdx.x == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_trace[blockIdx.x & 511][5] = smid;
     }
+#endif
 }
 #endif  // __CUDACC__
 

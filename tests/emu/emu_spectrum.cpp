@@ -11,6 +11,7 @@
 
 #include "../../rfanalyzer_b200/csrc/rfa_tables.h"
 #include "../../rfanalyzer_b200/csrc/spectrum_kernel.cuh"
+#include "../../rfanalyzer_b200/csrc/spectrum2_kernel.cuh"
 
 using namespace rfa;
 
@@ -107,10 +108,104 @@ int emu_size(int in_fmt, int out_kind, const SpectrumParams &p, float *peaks) {
     return -1;
 }
 
+// ---- dual-frame kernel (spectrum2_kernel.cuh): same schedule of frame pairs, thread by thread ----
+template <int NL, int IN, int PASS>
+struct EmuPasses2 {
+    using F = SpectrumFrame2<NL, IN>;
+    static void run(std::vector<c2> &x, const cf *tw, std::vector<std::array<cf, F::LAST_TW>> &TWR,
+                    std::vector<std::array<c2, 16>> &U) {
+        constexpr int T = Geom2<NL>::T;
+        if constexpr (PASS < Plan<NL>::PASSES) {
+            for (int tid = 0; tid < T; tid++) F::template scatter<PASS - 1>(x.data(), tid, U[tid].data());
+            for (int tid = 0; tid < T; tid++) {
+                if constexpr (PASS == F::LAST)
+                    F::gather_last_reg(x.data(), TWR[tid].data(), tid, U[tid].data());
+                else
+                    F::template gather<PASS>(x.data(), tw, tid, U[tid].data());
+            }
+            EmuPasses2<NL, IN, PASS + 1>::run(x, tw, TWR, U);
+        }
+    }
+};
+
+template <int NL, int IN>
+int emu_two(SpectrumParams p, float *peaks) {
+    using G = Geom2<NL>;
+    using F = SpectrumFrame2<NL, IN>;
+    constexpr int T = G::T, E = G::E, N = NL;
+    std::vector<cf> tw = make_pass_twiddles(NL);
+    p.tw = tw.data();
+    p.inv_n2 = -3.0102999566398120f * log2f((float)N);
+    std::vector<c2> x(Plan<NL>::SMEM_POINTS);
+    std::vector<std::array<c2, 16>> U(T);
+    std::vector<std::array<float, 16>> PK(T), W(T);
+    for (auto &a : PK) a.fill(-999999.0f);
+    for (int tid = 0; tid < T; tid++)
+        for (int r = 0; r < E; r++) W[tid][r] = (p.win ? p.win[tid + r * (NL / 16)] : 1.0f) * unit_scale<IN>();
+    std::vector<std::array<cf, F::LAST_TW>> TWR(T);
+    for (int tid = 0; tid < T; tid++) F::load_last_tw(tw.data(), tid, TWR[tid].data());
+    const long long npairs = (p.nframes + 1) / 2;
+    constexpr int BPS = in_elem_bytes<IN>();
+    for (long long v = 0; v < npairs; v++) {
+        const long long fB = p.nframes - 1 - 2 * v, fA = fB - 1;
+        for (int tid = 0; tid < T; tid++) {
+            uint32_t rawA[16], rawB[16];
+            F::load_raw((const char *)p.in + (fB * (long long)N + tid) * BPS, rawB);
+            F::load_raw((const char *)p.in + ((fA >= 0 ? fA : fB) * (long long)N + tid) * BPS, rawA);
+            F::first_from_raw(rawA, rawB, W[tid].data(), U[tid].data());
+        }
+        EmuPasses2<NL, IN, 1>::run(x, tw.data(), TWR, U);
+        for (int tid = 0; tid < T; tid++) {
+            float *outB = p.rows + frame_row(p, fB) * p.row_stride;
+            float *outA = p.rows + frame_row(p, fA >= 0 ? fA : fB) * p.row_stride;
+            const bool storeB = fB >= p.store_from, storeA = fA >= 0 && fA >= p.store_from;
+            if (peaks)
+                F::template emit<true>(outA, outB, storeA, storeB, tid, U[tid].data(), PK[tid].data(), p.inv_n2);
+            else
+                F::template emit<false>(outA, outB, storeA, storeB, tid, U[tid].data(), nullptr, p.inv_n2);
+        }
+    }
+    if (peaks) {
+        for (int i = 0; i < N; i++) peaks[i] = -999999.0f;
+        for (int tid = 0; tid < T; tid++)
+            for (int e = 0; e < E; e++) {
+                float &dst = peaks[F::peak_index(tid, e)];
+                dst = dst > PK[tid][e] ? dst : PK[tid][e];
+            }
+    }
+    if (p.avg)
+        for (int i = 0; i < N; i++) p.avg[i] = boxcar_average(p, i, [](const float *a) { return *a; });
+    return 0;
+}
+
+template <int NL>
+int emu_two_fmt(int in_fmt, const SpectrumParams &p, float *peaks) {
+    switch (in_fmt) {
+        case FMT_S8: return emu_two<NL, FMT_S8>(p, peaks);
+        case FMT_U8: return emu_two<NL, FMT_U8>(p, peaks);
+        case FMT_S16LE: return emu_two<NL, FMT_S16LE>(p, peaks);
+    }
+    return -1;
+}
+
 }  // namespace
+
+static int emu_dispatch(int N, int in_fmt, int out_kind, int window_kind, const void *in, const float *in_im,
+                        long long nframes, float *rows, float *peaks, float *avg, int L, bool dual, long long store_from);
 
 extern "C" int emu_spectrum_avg(int N, int in_fmt, int out_kind, int window_kind /* -1: none */, const void *in,
                                 const float *in_im, long long nframes, float *rows, float *peaks, float *avg, int L) {
+    return emu_dispatch(N, in_fmt, out_kind, window_kind, in, in_im, nframes, rows, peaks, avg, L, false, 0);
+}
+
+// the dual-frame kernel's path (N = 256 .. 4096, integer formats, dB rows)
+extern "C" int emu_spectrum2_avg(int N, int in_fmt, int window_kind, const void *in, long long nframes, float *rows,
+                                 float *peaks, float *avg, int L, long long store_from) {
+    return emu_dispatch(N, in_fmt, OUT_DB, window_kind, in, nullptr, nframes, rows, peaks, avg, L, true, store_from);
+}
+
+static int emu_dispatch(int N, int in_fmt, int out_kind, int window_kind, const void *in, const float *in_im,
+                        long long nframes, float *rows, float *peaks, float *avg, int L, bool dual, long long store_from) {
     SpectrumParams p{};
     std::vector<float> win;
     if (window_kind >= 0) {
@@ -126,12 +221,22 @@ extern "C" int emu_spectrum_avg(int N, int in_fmt, int out_kind, int window_kind
     p.ring_rows = 0;
     p.row_stride = out_kind == OUT_CPLX ? 2LL * N : N;
     p.nframes = nframes;
-    p.store_from = 0;
+    p.store_from = store_from;
     p.avg = avg;
     p.avg_len = L;
     p.avg_newest = nframes - 1;
     p.avg_dir = -1;
     p.avg_valid = nframes;
+    if (dual) {
+        switch (N) {
+            case 256: return emu_two_fmt<256>(in_fmt, p, peaks);
+            case 512: return emu_two_fmt<512>(in_fmt, p, peaks);
+            case 1024: return emu_two_fmt<1024>(in_fmt, p, peaks);
+            case 2048: return emu_two_fmt<2048>(in_fmt, p, peaks);
+            case 4096: return emu_two_fmt<4096>(in_fmt, p, peaks);
+        }
+        return -1;
+    }
     switch (N) {
         case 16: return emu_size<16, 1>(in_fmt, out_kind, p, peaks);
         case 32: return emu_size<32, 1>(in_fmt, out_kind, p, peaks);

@@ -71,3 +71,48 @@ def test_planar_windowed_entry(emu, oracle):
     mag = np.empty(n, np.float32)
     assert oracle.lib().orc_windowed_fft_logmag(re, im, n, n, n, mag) == 1
     assert np.abs(rows[0] - mag).max() < 0.01
+
+
+# ---- dual-frame kernel (spectrum2_kernel.cuh): two consecutive frames per thread, N = 256 .. 4096 ----
+def run_emu2(emu, n, fmt, window, x, frames, avg_len=1, store_from=0):
+    rows = np.full((frames, n), 7.0, np.float32)
+    peaks = np.zeros(n, np.float32)
+    avg = np.zeros(n, np.float32)
+    rc = emu.emu_spectrum2_avg(n, fmt, window, x.ctypes.data, frames, rows.ctypes.data, peaks.ctypes.data,
+                               avg.ctypes.data, avg_len, store_from)
+    assert rc == 0
+    return rows, peaks, avg
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("n,frames", [(256, 4), (512, 5), (1024, 3), (2048, 2), (4096, 3), (4096, 1)])
+def test_dual_frame_path_vs_oracle(emu, oracle, fmt, n, frames):
+    """Even and odd frame counts (an odd count leaves the oldest frame without a partner)."""
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows, peaks, avg = run_emu2(emu, n, fmt, 0, iq, frames)
+    r, p, a = oracle.spectrum_run(fmt, iq, n, 1)
+    assert np.abs(rows - r).max() < 0.01
+    assert np.abs(peaks - p).max() < 0.01
+    assert np.abs(avg - a).max() < 0.01
+    lin, lin_ref = 10.0 ** (rows / 5.0), 10.0 ** (r / 5.0)
+    assert np.all(np.abs(lin - lin_ref) <= 1e-4 * lin_ref + 1e-6 * lin_ref.max())
+
+
+def test_dual_frame_matches_single_frame_kernel(emu, oracle):
+    """Both kernels run the same butterflies in the same order (only the rounding of the twiddle
+    products differs): rows agree far inside the parity tolerance."""
+    n, frames = 2048, 5
+    iq = oracle.synth_iq(0, n * frames)
+    rows1, peaks1, _ = run_emu(emu, n, 0, 0, 0, iq, frames, want_peaks=True, avg_len=1)
+    rows2, peaks2, _ = run_emu2(emu, n, 0, 0, iq, frames)
+    assert np.abs(rows1 - rows2).max() < 2e-4 and np.abs(peaks1 - peaks2).max() < 2e-4
+
+
+def test_dual_frame_store_from(emu, oracle):
+    """Rows of frames below store_from stay untouched, peaks still cover every frame."""
+    n, frames = 1024, 5
+    iq = oracle.synth_iq(1, n * frames)
+    rows, peaks, _ = run_emu2(emu, n, 1, 0, iq, frames, store_from=2)
+    r, p, _ = oracle.spectrum_run(1, iq, n, 1)
+    assert np.all(rows[:2] == 7.0)
+    assert np.abs(rows[2:] - r[2:]).max() < 0.01 and np.abs(peaks - p).max() < 0.01

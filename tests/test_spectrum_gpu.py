@@ -237,3 +237,58 @@ def test_full_size_properties(gpu_ctx, oracle):
     for f in (0, 1, 777, 2048, 4095):
         r, _, _ = oracle.spectrum_run(0, iq[f * n * 2:(f + 1) * n * 2], n, 0)
         assert np.abs(rows[f].cpu().numpy() - r[0]).max() < DB_TOL
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("n,frames", [(256, 37), (512, 64), (1024, 37), (2048, 36), (4096, 37), (4096, 1), (4096, 600)])
+def test_dual_frame_kernel_vs_oracle(gpu_ctx, oracle, monkeypatch, fmt, n, frames):
+    """spectrum2_kernel (two frames per thread, RFA_DUAL=1): same contract, odd and even frame counts,
+    fewer and more frame pairs than CTAs."""
+    monkeypatch.setenv("RFA_DUAL", "1")
+    iq = oracle.synth_iq(fmt, n * frames)
+    r, p, a = oracle.spectrum_run(fmt, iq, n, 3)
+    launches = gpu_ctx.launch_count
+    rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
+    assert gpu_ctx.launch_count > launches
+    assert np.abs(rows - r).max() < DB_TOL
+    assert np.abs(peaks - p).max() < DB_TOL
+    assert np.abs(avg - a).max() < DB_TOL
+    assert lin_ok(rows, r)
+    assert np.array_equal(rows.argmax(axis=1), r.argmax(axis=1))
+    assert np.array_equal(peaks, rows.max(axis=0))
+
+
+def test_dual_frame_kernel_ring_and_history(gpu_ctx, oracle, monkeypatch):
+    """The reference's backwards ring with more frames than rows, through the dual-frame kernel."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    monkeypatch.setenv("RFA_DUAL", "1")
+    n, L, ring = 1024, 5, 300
+    L_o = oracle.lib()
+    proc = L_o.orc_fftproc_new(ring, 1)
+    plan = rfa.SpectrumPlan(gpu_ctx, 1, n, avg_len=L)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
+        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
+        write_index, history, first = 0, 0, 0
+        for call, frames in enumerate((3, 1, 311, 8)):
+            iq = oracle.synth_iq(1, n * frames, first=first)
+            first += n * frames
+            r, _, _ = oracle.spectrum_run(1, iq, n, 0)
+            for k in range(frames):
+                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
+            plan.process(torch.from_numpy(iq).cuda(), frames, rows=d_ring, peaks=d_peaks, avg=d_avg,
+                         row0=write_index, row_step=-1, ring_rows=ring, history_rows=history,
+                         peaks_accumulate=call > 0)
+            gpu_ctx.sync()
+            write_index = (write_index - frames) % ring
+            history = min(ring, history + frames)
+            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
+            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
+            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
+            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
+            avg_ref = np.empty(n, np.float32)
+            L_o.orc_time_average(proc, L, avg_ref)
+            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
+    L_o.orc_fftproc_free(proc)
