@@ -277,15 +277,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         total_ms = float(ms.item())
 
-        # ---- kernel-only duration (roofline numerator): events around each launch ---------------
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-               for _ in range(min(args.steps, 50))]
-        for k, (a, b) in enumerate(kev):
-            a.record(stream)
+        # ---- kernel-only duration (roofline numerator): one event pair around a back-to-back batch of the
+        # fused kernel's launches on its own stream (no collective, no host work in between) -------------
+        nk = min(args.steps, 100)
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ka.record(stream)
+        for k in range(nk):
             plan.process(iqs[k % NBUF], FRAMES, rows=rows[k % NBUF], peaks=peaks, avg=avg, peaks_accumulate=True)
-            b.record(stream)
+        kb.record(stream)
         stream.synchronize()
-        kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+        kernel_ms = ka.elapsed_time(kb) / nk
 
     # ---- end to end: pinned host buffers through the public API ---------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 20)
@@ -338,7 +339,8 @@ def main():
                          "frac": achieved / peak_gbs, "traffic": ncu_traffic(),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_us_per_launch": kernel_ms * 1e3,
                          "peak_source": peak_src,
-                         "note": "4096-pt FFT at 6 B/sample is FP32-issue bound on B200, see DESIGN.md"},
+                         "note": "at 6 B/sample the 4096-pt FFT is bound by the FP32 pipe (48% busy) and the shared-memory "
+                                 "pipe (51% busy) together, not by HBM: DESIGN.md 4.1, profiles/r01b_*"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -348,13 +350,14 @@ def main():
                 cores = host_cores()
                 if O.ref_available():
                     one, t_one = cpu_reference_pass(h, 1, 3)
-                    passes = max(2, int(12.0 / max(t_one / 3 / cores * 1.3, 1e-3) / 8))
-                    passes = min(passes, 12)
+                    est = max(t_one / 3 / cores * 1.5, 1e-3)       # seconds per all-core pass, guessed
+                    passes = max(4, min(400, int(10.0 / est)))     # about 10 s of CPU work
+                    cpu_reference_pass(h, cores, 2)                # threads and pages warm
                     allc, t_all = cpu_reference_pass(h, cores, passes)
                     out["cpu_baseline"] = {"value": allc, "unit": UNIT, "cores": cores, "kind": "reference",
                                            "single_thread_value": one,
                                            "sample": "full 2^24-sample recording: 3 passes on 1 thread (%.1f s), "
-                                                     "%d passes on %d threads (%.1f s)" % (t_one, passes, cores, t_all)}
+                                                     "%d passes on all %d threads (%.1f s)" % (t_one, passes, cores, t_all)}
                 else:
                     t0 = time.perf_counter()
                     O.spectrum_run(FMT_S8, h, N_FFT, AVG_LEN)
