@@ -266,7 +266,21 @@ __global__ void __launch_bounds__(256, 1) spectrum2_kernel(const SpectrumParams 
     }
 
     RFA_STAMP(2);
-    if (want_peak && worked) {
+    if constexpr (FPC > 1) {  // see spectrum_kernel: one atomic per bin per CTA
+        if (want_peak) {
+            float *red = reinterpret_cast<float *>(smem_raw);
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; e++) red[sub * NL + F::peak_index(tid, e)] = worked ? pk[e] : -999999.0f;
+            __syncthreads();
+            for (int i = threadIdx.x; i < NL; i += G::CTA) {
+                float m = red[i];
+#pragma unroll
+                for (int k = 1; k < FPC; k++) m = fmaxf(m, red[k * NL + i]);
+                if (m > -999999.0f) atomic_max_float(p.peaks + i, m);
+            }
+        }
+    } else if (want_peak && worked) {
 #pragma unroll
         for (int e = 0; e < E; e++) atomic_max_float(p.peaks + F::peak_index(tid, e), pk[e]);
     }

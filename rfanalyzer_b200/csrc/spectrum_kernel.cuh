@@ -545,7 +545,23 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     }
 
     RFA_STAMP(2);  // main loop done
-    if (want_peak && worked) {
+    if constexpr (FPC > 1) {
+        // several frame slots per CTA hold the same bins: reduce them in shared memory first, then
+        // one atomic per bin per CTA (at N = 256 the 16 slots otherwise queue 4736 atomics per bin)
+        if (want_peak) {
+            float *red = reinterpret_cast<float *>(smem_raw);  // [FPC][NL], the exchange frames are free now
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; e++) red[sub * NL + F::peak_index(c, tid, e)] = worked ? pk[e] : -999999.0f;
+            __syncthreads();
+            for (int i = threadIdx.x; i < NL; i += G::CTA) {
+                float m = red[i];
+#pragma unroll
+                for (int k = 1; k < FPC; k++) m = fmaxf(m, red[k * NL + i]);
+                if (m > -999999.0f) atomic_max_float(p.peaks + i, m);
+            }
+        }
+    } else if (want_peak && worked) {
 #pragma unroll
         for (int e = 0; e < E; e++) atomic_max_float(p.peaks + F::peak_index(c, tid, e), pk[e]);
     }
