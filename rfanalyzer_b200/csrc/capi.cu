@@ -516,7 +516,13 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
     RFA_REQUIRE(mem == RFA_MEM_HOST, "unknown memory space %d", mem);
     RFA_REQUIRE(!o->rows || o->ring_rows == 0, "ring-buffer rows must be device resident");
     const size_t frame_in = (size_t)n * bps, frame_out = (size_t)n * sizeof(float);
-    long long cf_frames = (long long)((8u << 20) / frame_in);  // ~8 MiB of IQ per chunk
+    // IQ bytes per chunk: small enough that the first copy in and the last copy out (which overlap with
+    // nothing) are short, large enough that the per-chunk launch and copy set-up costs stay hidden
+    static const size_t chunk_bytes = [] {
+        const char *e = getenv("RFA_CHUNK_KIB");  // tuning runs
+        return (size_t)(e && atoi(e) > 0 ? atoi(e) : 4096) << 10;
+    }();
+    long long cf_frames = (long long)(chunk_bytes / frame_in);
     if (cf_frames < L + 1) cf_frames = L + 1;
     if (cf_frames > nframes) cf_frames = nframes;
     const long long nchunks = nframes / cf_frames;  // the last chunk also takes the remainder

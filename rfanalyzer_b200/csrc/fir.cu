@@ -126,6 +126,225 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
     }
 }
 
+// ---- K4 (+K2), fast path (RFA_SUM_FMA) --------------------------------------------------------
+// Same outputs as resample_kernel<KIND,false> up to the order of the float32 additions.
+//  * staging: four input samples per thread and step (one 64/128-bit load of raw codes), NCO phase
+//    advanced incrementally (no 64-bit modulo per sample), re/im interleaved in shared memory;
+//  * dot products: G lanes share one output, lane g takes taps g, g+G, ... (neighbouring lanes read
+//    neighbouring samples and taps: conflict-free, coalesced), one LDS.64 + one packed FFMA2 per tap
+//    and sample, then a shuffle reduction.  G is chosen by the launcher so that a tile's outputs
+//    times G fill the CTA (a 625/6 decimation yields only 54 outputs per staged span).
+//  * the polyphase bank sits in shared memory when it fits.
+struct ResampleFastArgs {
+    ResampleArgs a;
+    int G;          // lanes per output: 1, 2, 4, ... 32
+    int bank_smem;  // bank floats copied to shared memory (0 = read through L1)
+};
+
+template <int KIND>
+__device__ __forceinline__ void stage4(const StreamSrc &s, long long k, int t, float2 *dst) {
+    // four consecutive stream samples k .. k+3 (k >= 0, k % 4 == 0), NCO index of sample k is t
+    float r[4], q[4];
+    if (KIND == FMT_S8 || KIND == FMT_U8) {
+        const uint2 w = *reinterpret_cast<const uint2 *>((const char *)s.raw + k * 2);
+        const uint32_t c[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (KIND == FMT_S8) {
+                r[i] = conv_s8((int)(int8_t)(c[i] & 0xFF));
+                q[i] = conv_s8((int)(int8_t)(c[i] >> 8));
+            } else {
+                r[i] = conv_u8((int)(c[i] & 0xFF));
+                q[i] = conv_u8((int)(c[i] >> 8));
+            }
+        }
+    } else if (KIND == FMT_S16LE) {
+        const uint4 w = *reinterpret_cast<const uint4 *>((const char *)s.raw + k * 4);
+        const uint32_t c[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            r[i] = conv_s16((int)(int16_t)(c[i] & 0xFFFF));
+            q[i] = conv_s16((int)(int16_t)(c[i] >> 16));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            r[i] = s.re[k + i];
+            q[i] = s.im ? s.im[k + i] : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (KIND != 3 && s.nco_cos) {
+            int ti = t + i;
+            while (ti >= s.nco_len) ti -= s.nco_len;
+            const float c = __ldg(s.nco_cos + ti), sn = __ldg(s.nco_sin + ti);
+            dst[i] = make_float2(__fsub_rn(__fmul_rn(r[i], c), __fmul_rn(q[i], sn)),
+                                 __fadd_rn(__fmul_rn(q[i], c), __fmul_rn(r[i], sn)));
+        } else {
+            dst[i] = make_float2(r[i], q[i]);
+        }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void stage_span(const StreamSrc &src, long long k_al, int span, float2 *xs) {
+    const int nco_len = src.nco_len > 0 ? src.nco_len : 1;
+    // NCO index of sample k_al + 4*threadIdx.x, then advanced by 4*blockDim.x per step
+    long long t0 = ((long long)src.nco_idx + k_al + 4LL * threadIdx.x) % nco_len;
+    if (t0 < 0) t0 += nco_len;
+    int t = (int)t0;
+    const int tstep = (int)((4LL * blockDim.x) % nco_len);
+    for (int sidx = 4 * threadIdx.x; sidx < span; sidx += 4 * blockDim.x) {
+        const long long k = k_al + sidx;
+        if (k >= 0 && sidx + 3 < span) {
+            stage4<KIND>(src, k, t, xs + sidx);
+        } else {  // history (and the zeros before it), and the last samples of the span: scalar path
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (sidx + i >= span) break;
+                float r, q;
+                fetch<KIND>(src, k + i, r, q);
+                xs[sidx + i] = make_float2(r, q);
+            }
+        }
+        t += tstep;
+        if (t >= nco_len) t -= nco_len;
+    }
+}
+
+template <int KIND, bool BANK_SMEM>
+__global__ void __launch_bounds__(256) resample_fast_kernel(const ResampleFastArgs fa) {
+    const ResampleArgs &a = fa.a;
+    extern __shared__ float2 xs[];  // [span_max + 8] samples, then the bank
+    float *sbank = reinterpret_cast<float *>(xs + a.span_max + 8);
+    const long long j0 = (long long)blockIdx.x * a.tile;
+    long long j1 = j0 + a.tile;
+    if (j1 > a.nout) j1 = a.nout;
+    if (j0 >= j1) return;
+    const long long k_first = a.rel + ((long long)a.ph0 + j0 * a.D) / a.I;
+    const long long k_hi = a.rel + ((long long)a.ph0 + (j1 - 1) * a.D) / a.I;
+    const long long k_lo = k_first - (a.nt - 1);
+    // stage [k_al, k_hi], k_al = k_lo rounded down to a multiple of 4 (floor also for negatives)
+    const long long k_al = k_lo - (((k_lo % 4) + 4) % 4);
+    const int span = (int)(k_hi - k_al + 1);
+    if (BANK_SMEM)
+        for (int i = threadIdx.x; i < fa.bank_smem; i += blockDim.x) sbank[i] = a.bank[i];
+    stage_span<KIND>(a.src, k_al, span, xs);
+    __syncthreads();
+    const int G = fa.G, g = threadIdx.x & (G - 1), grp = threadIdx.x / G, ngrp = blockDim.x / G;
+    for (long long jb = j0; jb < j1; jb += ngrp) {  // warp-uniform trip count (the shuffles below)
+        const long long j = jb + grp;
+        const bool valid = j < j1;
+        const long long T = (long long)a.ph0 + (valid ? j : j0) * a.D;
+        const int pos = (int)(a.rel + T / a.I - k_al);
+        const size_t tap0 = (size_t)(T % a.I) * a.nt;
+        const float *taps = BANK_SMEM ? sbank + tap0 : a.bank + tap0;  // two address spaces, two code paths
+        const float2 *x = xs + pos;
+        cf acc = cf{0.0f, 0.0f}, acc2 = cf{0.0f, 0.0f};
+        int t = valid ? g : a.nt;
+        for (; t + G < a.nt; t += 2 * G) {  // two independent chains
+            const float2 x0 = x[-t], x1 = x[-(t + G)];
+            const float h0 = BANK_SMEM ? taps[t] : __ldg(taps + t), h1 = BANK_SMEM ? taps[t + G] : __ldg(taps + t + G);
+            acc = caxpy(h0, cf{x0.x, x0.y}, acc);
+            acc2 = caxpy(h1, cf{x1.x, x1.y}, acc2);
+        }
+        if (t < a.nt) {
+            const float2 x0 = x[-t];
+            acc = caxpy(BANK_SMEM ? taps[t] : __ldg(taps + t), cf{x0.x, x0.y}, acc);
+        }
+        acc = cadd(acc, acc2);
+        for (int d = G >> 1; d > 0; d >>= 1) {
+            acc.x += __shfl_xor_sync(0xFFFFFFFFu, acc.x, d);
+            acc.y += __shfl_xor_sync(0xFFFFFFFFu, acc.y, d);
+        }
+        if (g == 0 && valid) {
+            a.out_re[j] = acc.x;
+            a.out_im[j] = acc.y;
+        }
+    }
+}
+
+// ---- K4 (+K2), register-tiled path for moderate decimation (taps per phase > D) -----------------
+// Outputs of one polyphase share their taps and their windows slide by exactly D samples, so with
+// t = a*D + b the sum  y[m] = sum_t h[t] x[pos0 + m*D - t]  becomes, for every b, a short convolution
+// over (a, m) of h_b[a] = h[a*D + b] with s_b[n] = x[pos0 - b + n*D].  One thread owns M consecutive
+// outputs of one phase: per b it loads M + A - 1 samples and A taps and issues M*A packed FFMA2 --
+// about three times fewer shared-memory loads per FMA than one load pair per tap, and with M*D odd
+// the sample loads of a half-warp fall into distinct banks.  The taps are transposed to [phase][b][a]
+// in shared memory (zero-padded to AP per b) so that a thread reads them with 128-bit broadcasts.
+struct ResampleTiledArgs {
+    ResampleArgs a;  // a.tile = I * M * B outputs per CTA
+    int B;           // blocks of M same-phase outputs per phase and CTA
+    int A;           // ceil(nt / D) <= AMAX
+    int AP;          // A rounded up to a multiple of 4
+};
+
+template <int KIND, int M, int AMAX>
+__global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiledArgs ta) {
+    const ResampleArgs &a = ta.a;
+    constexpr int AP = (AMAX + 3) & ~3;
+    extern __shared__ float2 xs[];  // [span_max + 8] samples, then the transposed bank [I][D][AP]
+    float *hT = reinterpret_cast<float *>(xs + a.span_max + 8);
+    const long long j0 = (long long)blockIdx.x * a.tile;
+    if (j0 >= a.nout) return;
+    const int nq = ta.B * M;  // outputs per phase in this tile
+    // stream window of the tile: the newest sample belongs to the last output of the residue with the
+    // largest offset, the oldest to tap index A*D - 1 of output j0
+    const long long k_first = a.rel + ((long long)a.ph0 + j0 * a.D) / a.I;
+    long long k_hi = a.rel + ((long long)a.ph0 + (j0 + a.I - 1) * a.D) / a.I + (long long)(nq - 1) * a.D;
+    const long long k_end = a.rel + ((long long)a.ph0 + (a.nout - 1) * a.D) / a.I;  // newest sample any output needs
+    if (k_hi > k_end) k_hi = k_end;  // last tile: never read past the input
+    const long long k_lo = k_first - ((long long)ta.A * a.D - 1);
+    const long long k_al = k_lo - (((k_lo % 4) + 4) % 4);
+    const int span = (int)(k_hi - k_al + 1);
+    for (int i = threadIdx.x; i < a.I * a.D * AP; i += blockDim.x) {
+        const int aa = i % AP, pb = i / AP, b = pb % a.D, p = pb / a.D, t = aa * a.D + b;
+        hT[i] = (aa < ta.A && t < a.nt) ? a.bank[(size_t)p * a.nt + t] : 0.0f;
+    }
+    stage_span<KIND>(a.src, k_al, span, xs);
+    __syncthreads();
+    for (int task = threadIdx.x; task < a.I * ta.B; task += blockDim.x) {
+        const int r = task / ta.B, qb = task - r * ta.B;
+        const long long T = (long long)a.ph0 + (j0 + r) * a.D;
+        const int phase = (int)(T % a.I);
+        const int pos0 = (int)(a.rel + T / a.I - k_al) + qb * M * a.D;
+        cf acc[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) acc[m] = cf{0.0f, 0.0f};
+        const float *hp = hT + (size_t)phase * a.D * AP;
+        for (int b = 0; b < a.D; b++) {
+            float h[AP];
+#pragma unroll
+            for (int v = 0; v < AP / 4; v++) {
+                const float4 w = *reinterpret_cast<const float4 *>(hp + b * AP + 4 * v);
+                h[4 * v] = w.x, h[4 * v + 1] = w.y, h[4 * v + 2] = w.z, h[4 * v + 3] = w.w;
+            }
+            const float2 *sp = xs + pos0 - b;
+            cf sv[M + AMAX - 1];  // sv[i] = s_b[i - (AMAX - 1)]
+#pragma unroll
+            for (int i = 0; i < M + AMAX - 1; i++) {
+                const int n = i - (AMAX - 1);
+                // taps a >= A are zero, their samples may lie before the staged span: do not touch them
+                const float2 x = (n >= -(ta.A - 1)) ? sp[n * a.D] : make_float2(0.0f, 0.0f);
+                sv[i] = cf{x.x, x.y};
+            }
+#pragma unroll
+            for (int aa = 0; aa < AMAX; aa++)
+#pragma unroll
+                for (int m = 0; m < M; m++) acc[m] = caxpy(h[aa], sv[m - aa + AMAX - 1], acc[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            const long long j = j0 + (long long)(qb * M + m) * a.I + r;
+            if (j < a.nout) {
+                a.out_re[j] = acc[m].x;
+                a.out_im[j] = acc[m].y;
+            }
+        }
+    }
+}
+
 // ---- K5 ------------------------------------------------------------------------------------
 struct FirArgs {
     StreamSrc src;
@@ -242,6 +461,111 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
     a.out_im = out_im;
     const unsigned grid = (unsigned)((nout + tile - 1) / tile);
     const size_t smem = 2 * (size_t)kSpanMax * sizeof(float);
+    const bool aligned = in.kind == 3 || ((size_t)in.raw & 15) == 0;  // the fast paths load 64/128-bit groups
+    const int A = (nt + D - 1) / D;
+    if (!exact && aligned && A >= 2 && A <= 12 && (size_t)I * D * 12 <= 8192) {
+        // register-tiled path: M = 9 outputs per thread, B blocks per phase
+        constexpr int M = 9, kSpanT = 7680;
+        long long B = ((long long)kSpanT - 8 - (long long)(A + 1) * D) / ((long long)M * D);  // span <= (B*M + A + 1)*D + 4
+        if (B >= 16) B -= B % 16;
+        if (B >= 1) {
+            ResampleTiledArgs ta{};
+            ta.a = a;
+            ta.a.span_max = kSpanT;
+            ta.a.tile = (int)((long long)I * M * B);
+            ta.B = (int)B;
+            ta.A = A;
+            const int amax = A <= 3 ? 3 : (A <= 5 ? 5 : (A <= 9 ? 9 : 12));
+            ta.AP = (amax + 3) & ~3;
+            const unsigned tgrid = (unsigned)((nout + ta.a.tile - 1) / ta.a.tile);
+            long long threads = ((long long)I * B + 31) / 32 * 32;
+            if (threads > 256) threads = 256;
+            const size_t tsmem = ((size_t)kSpanT + 8) * sizeof(float2) + (size_t)I * D * ta.AP * sizeof(float);
+            static bool tconfigured = false;
+            const int mx = (int)(((size_t)kSpanT + 8) * sizeof(float2) + 8192 * sizeof(float));
+#define RFA_RT(KIND, AM)                                                                                           \
+    do {                                                                                                           \
+        if (!tconfigured)                                                                                          \
+            cudaFuncSetAttribute(resample_tiled_kernel<KIND, M, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); \
+        if (launch_now) resample_tiled_kernel<KIND, M, AM><<<tgrid, (unsigned)threads, tsmem, st>>>(ta);            \
+    } while (0)
+#define RFA_RT_ALL(AM)                               \
+    do {                                             \
+        RFA_RT(0, AM);                               \
+        RFA_RT(1, AM);                               \
+        RFA_RT(2, AM);                               \
+        RFA_RT(3, AM);                               \
+    } while (0)
+            if (!tconfigured) {  // opt every instantiation in to the large shared-memory carve-out once
+                const bool launch_now = false;
+                RFA_RT_ALL(3);
+                RFA_RT_ALL(5);
+                RFA_RT_ALL(9);
+                RFA_RT_ALL(12);
+                tconfigured = true;
+            }
+            {
+                const bool launch_now = true;
+#define RFA_RT_KIND(AM)                                  \
+    switch (in.kind) {                                   \
+        case 0: RFA_RT(0, AM); break;                    \
+        case 1: RFA_RT(1, AM); break;                    \
+        case 2: RFA_RT(2, AM); break;                    \
+        case 3: RFA_RT(3, AM); break;                    \
+        default: return cudaErrorInvalidValue;           \
+    }
+                if (amax == 3) { RFA_RT_KIND(3) }
+                else if (amax == 5) { RFA_RT_KIND(5) }
+                else if (amax == 9) { RFA_RT_KIND(9) }
+                else { RFA_RT_KIND(12) }
+#undef RFA_RT_KIND
+            }
+#undef RFA_RT_ALL
+#undef RFA_RT
+            return cudaGetLastError();
+        }
+    }
+    if (!exact && aligned) {
+        ResampleFastArgs fa{};
+        fa.a = a;
+        // lanes per output: one when a tile has enough outputs for every thread, otherwise 16 -- a
+        // half-warp per output reads 16 neighbouring samples, which is conflict-free whatever the
+        // distance between the windows of neighbouring outputs
+        const int G = (tile >= 256 && nout >= 256) ? 1 : 16;
+        fa.G = G;
+        const size_t bank_floats = (size_t)I * nt;
+        fa.bank_smem = bank_floats * sizeof(float) <= 32 * 1024 ? (int)bank_floats : 0;
+        const size_t fsmem = ((size_t)kSpanMax + 8) * sizeof(float2) + (size_t)fa.bank_smem * sizeof(float);
+        static bool fconfigured = false;
+        if (!fconfigured) {
+            const int mx = (int)(((size_t)kSpanMax + 8) * sizeof(float2) + 32 * 1024);
+            cudaFuncSetAttribute(resample_fast_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(resample_fast_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(resample_fast_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(resample_fast_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(resample_fast_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(resample_fast_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(resample_fast_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            cudaFuncSetAttribute(resample_fast_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+            fconfigured = true;
+        }
+#define RFA_RF(KIND)                                                                          \
+    do {                                                                                      \
+        if (fa.bank_smem)                                                                     \
+            resample_fast_kernel<KIND, true><<<grid, 256, fsmem, st>>>(fa);                   \
+        else                                                                                  \
+            resample_fast_kernel<KIND, false><<<grid, 256, fsmem, st>>>(fa);                  \
+    } while (0)
+        switch (in.kind) {
+            case 0: RFA_RF(0); break;
+            case 1: RFA_RF(1); break;
+            case 2: RFA_RF(2); break;
+            case 3: RFA_RF(3); break;
+            default: return cudaErrorInvalidValue;
+        }
+#undef RFA_RF
+        return cudaGetLastError();
+    }
 #define RFA_RS(KIND)                                                                              \
     do {                                                                                          \
         if (exact)                                                                                \

@@ -159,6 +159,34 @@ def test_resampler_streaming_bit_exact(gpu_ctx, oracle, i, d, maxtaps):
     L.orc_resampler_free(orr)
 
 
+@pytest.mark.parametrize("i,d,maxtaps", [(4, 25, 500), (1, 25, 500), (2, 5, 500), (6, 625, 500), (12, 625, 500),
+                                         (11, 17, 0), (17, 11, 0), (3, 2, 0), (4, 50, 500)])
+def test_resampler_fast_paths_vs_oracle(gpu_ctx, oracle, i, d, maxtaps):
+    """RFA_SUM_FMA selects the register-tiled kernel (taps per phase > D) or the lanes-per-output kernel:
+    same counters and state as the exact kernel, samples within the demodulated-audio tolerance
+    (the additions are reordered, every product is the same)."""
+    import rfanalyzer_b200 as rfa
+    L = oracle.lib()
+    orr = L.orc_resampler_new(i, d, None, 0, 0.4, maxtaps)
+    grr = rfa.RationalResampler(gpu_ctx, i, d, maxTaps=maxtaps, flags=rfa.SUM_FMA)
+    rng = np.random.default_rng(i * 1000 + d)
+    for n, cap in ((8192, 8192 * 2), (1, 4), (999, 4000), (20000, 50), (7, 100), (70011, 140000), (65536, 140000)):
+        re = rng.standard_normal(n).astype(np.float32)
+        im = rng.standard_normal(n).astype(np.float32)
+        pin = oracle.PacketView(n).load(re, im, 2400000)
+        pout = oracle.PacketView(cap)
+        want = L.orc_resampler_resample(orr, pin.p, pout.p, 0, n)
+        out = rfa.SamplePacket(cap)
+        got = grr.resample(rfa.SamplePacket(re, im, 0, 2400000), out, 0, n)
+        assert got == want and out.size() == pout.size
+        if out.size():
+            wr, wi = pout.out_re(), pout.out_im()
+            peak = max(np.abs(wr).max(), np.abs(wi).max(), 1e-30)
+            assert np.abs(out.re()[: out.size()] - wr).max() <= 1e-5 * peak + 1e-7
+            assert np.abs(out.im()[: out.size()] - wi).max() <= 1e-5 * peak + 1e-7
+    L.orc_resampler_free(orr)
+
+
 def _quad_packets(oracle, mode, npackets, n):
     """complex packets at the mode's quadrature rate: a modulated carrier plus noise"""
     rng = np.random.default_rng(mode)
