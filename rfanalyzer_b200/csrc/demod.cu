@@ -97,18 +97,37 @@ __global__ void __launch_bounds__(256) packet_stats_kernel(const float *__restri
 
 // Demodulator.kt:290,296,299-302 (AM) and :347-355 (SSB/CW): the AGC recurrence over packets.
 // state[0] = lastMax carried between calls.  mean[p] only matters for AM.
-__global__ void agc_scan_kernel(const long long *off, int npackets, const float *sum, const float *mx,
-                                float *state, float *gain, float *mean) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float last = state[0];
-    for (int p = 0; p < npackets; p++) {
-        last = __fmul_rn(last, (float)0.95);
-        if (mx[p] > last) last = mx[p];
-        gain[p] = __fdiv_rn(0.75f, last);
-        const long long n = off[p + 1] - off[p];
-        mean[p] = __fdiv_rn(sum[p], (float)n);
+// One CTA: the packet maxima go through shared memory in blocks of 1024, thread 0 runs the
+// recurrence on them (the only sequential part, a few cycles per packet), everybody divides.
+__global__ void __launch_bounds__(256) agc_scan_kernel(const long long *off, int npackets, const float *sum,
+                                                       const float *mx, float *state, float *gain, float *mean) {
+    __shared__ float s_last[1024];
+    __shared__ float s_carry;
+    if (threadIdx.x == 0) s_carry = state[0];
+    for (int p0 = 0; p0 < npackets; p0 += 1024) {
+        const int np = npackets - p0 < 1024 ? npackets - p0 : 1024;
+        for (int i = threadIdx.x; i < np; i += blockDim.x) s_last[i] = mx[p0 + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float last = s_carry;
+            for (int i = 0; i < np; i++) {
+                last = __fmul_rn(last, (float)0.95);
+                const float m = s_last[i];
+                if (m > last) last = m;
+                s_last[i] = last;
+            }
+            s_carry = last;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            const int p = p0 + i;
+            gain[p] = __fdiv_rn(0.75f, s_last[i]);
+            const long long n = off[p + 1] - off[p];
+            mean[p] = __fdiv_rn(sum[p], (float)n);
+        }
+        __syncthreads();
     }
-    state[0] = last;
+    if (threadIdx.x == 0) state[0] = s_carry;
 }
 
 // out = (x - mean[p]) * gain[p] * volume (AM) or x * gain[p] * volume (SSB/CW); one block row per packet
@@ -162,7 +181,7 @@ cudaError_t agc_launch(float *x, const long long *off, int npackets, long long m
         packet_stats_kernel<true><<<(npackets + 63) / 64, 64, 0, st>>>(x, off, npackets, sum, mx);
     else
         packet_stats_kernel<false><<<npackets, 256, 0, st>>>(x, off, npackets, sum, mx);
-    agc_scan_kernel<<<1, 32, 0, st>>>(off, npackets, sum, mx, state, gain, mean);
+    agc_scan_kernel<<<1, 256, 0, st>>>(off, npackets, sum, mx, state, gain, mean);
     unsigned bx = (unsigned)((max_packet + 255) / 256);
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;

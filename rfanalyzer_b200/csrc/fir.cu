@@ -18,6 +18,7 @@
 // (no FMA), which reproduces the JVM's float32 results bit for bit; SUM_FMA fuses them.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "rfa_fft_core.cuh"
@@ -141,13 +142,32 @@ struct ResampleFastArgs {
     int bank_smem;  // bank floats copied to shared memory (0 = read through L1)
 };
 
+// four consecutive stream samples k .. k+3 (k >= 0, k % 4 == 0): raw words first (so that several
+// groups' loads are in flight before any is converted), then conversion + NCO mixing
+struct Raw4 {
+    uint4 w;    // raw codes (8-bit kinds use x, y) or, for planar floats, the four re values
+    float4 im;  // planar floats: the four im values
+};
 template <int KIND>
-__device__ __forceinline__ void stage4(const StreamSrc &s, long long k, int t, float2 *dst) {
-    // four consecutive stream samples k .. k+3 (k >= 0, k % 4 == 0), NCO index of sample k is t
+__device__ __forceinline__ Raw4 load4(const StreamSrc &s, long long k) {
+    Raw4 r;
+    if (KIND == FMT_S8 || KIND == FMT_U8) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>((const char *)s.raw + k * 2));
+        r.w = make_uint4(w.x, w.y, 0u, 0u);
+    } else if (KIND == FMT_S16LE) {
+        r.w = __ldg(reinterpret_cast<const uint4 *>((const char *)s.raw + k * 4));
+    } else {
+        r.w = make_uint4(__float_as_uint(s.re[k]), __float_as_uint(s.re[k + 1]), __float_as_uint(s.re[k + 2]),
+                         __float_as_uint(s.re[k + 3]));
+        r.im = s.im ? make_float4(s.im[k], s.im[k + 1], s.im[k + 2], s.im[k + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return r;
+}
+template <int KIND>
+__device__ __forceinline__ void convert4(const StreamSrc &s, const Raw4 &raw, int t, float2 *dst) {
     float r[4], q[4];
     if (KIND == FMT_S8 || KIND == FMT_U8) {
-        const uint2 w = *reinterpret_cast<const uint2 *>((const char *)s.raw + k * 2);
-        const uint32_t c[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+        const uint32_t c[4] = {raw.w.x & 0xFFFFu, raw.w.x >> 16, raw.w.y & 0xFFFFu, raw.w.y >> 16};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             if (KIND == FMT_S8) {
@@ -159,19 +179,16 @@ __device__ __forceinline__ void stage4(const StreamSrc &s, long long k, int t, f
             }
         }
     } else if (KIND == FMT_S16LE) {
-        const uint4 w = *reinterpret_cast<const uint4 *>((const char *)s.raw + k * 4);
-        const uint32_t c[4] = {w.x, w.y, w.z, w.w};
+        const uint32_t c[4] = {raw.w.x, raw.w.y, raw.w.z, raw.w.w};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             r[i] = conv_s16((int)(int16_t)(c[i] & 0xFFFF));
             q[i] = conv_s16((int)(int16_t)(c[i] >> 16));
         }
     } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            r[i] = s.re[k + i];
-            q[i] = s.im ? s.im[k + i] : 0.0f;
-        }
+        r[0] = __uint_as_float(raw.w.x), r[1] = __uint_as_float(raw.w.y), r[2] = __uint_as_float(raw.w.z),
+        r[3] = __uint_as_float(raw.w.w);
+        q[0] = raw.im.x, q[1] = raw.im.y, q[2] = raw.im.z, q[3] = raw.im.w;
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -190,26 +207,39 @@ __device__ __forceinline__ void stage4(const StreamSrc &s, long long k, int t, f
 template <int KIND>
 __device__ __forceinline__ void stage_span(const StreamSrc &src, long long k_al, int span, float2 *xs) {
     const int nco_len = src.nco_len > 0 ? src.nco_len : 1;
-    // NCO index of sample k_al + 4*threadIdx.x, then advanced by 4*blockDim.x per step
+    // NCO index of sample k_al + 4*threadIdx.x, then advanced by 4*blockDim.x per group
     long long t0 = ((long long)src.nco_idx + k_al + 4LL * threadIdx.x) % nco_len;
     if (t0 < 0) t0 += nco_len;
     int t = (int)t0;
-    const int tstep = (int)((4LL * blockDim.x) % nco_len);
-    for (int sidx = 4 * threadIdx.x; sidx < span; sidx += 4 * blockDim.x) {
-        const long long k = k_al + sidx;
-        if (k >= 0 && sidx + 3 < span) {
-            stage4<KIND>(src, k, t, xs + sidx);
-        } else {  // history (and the zeros before it), and the last samples of the span: scalar path
+    const int tstep = (int)((4LL * blockDim.x) % nco_len), sstep = 4 * (int)blockDim.x;
+    constexpr int U = 4;  // groups in flight per thread: the staging is a chain of DRAM round trips otherwise
+    for (int s0 = 4 * threadIdx.x; s0 < span; s0 += U * sstep) {
+        Raw4 raw[U];
+        bool fast[U];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (sidx + i >= span) break;
-                float r, q;
-                fetch<KIND>(src, k + i, r, q);
-                xs[sidx + i] = make_float2(r, q);
-            }
+        for (int u = 0; u < U; u++) {
+            const int sidx = s0 + u * sstep;
+            const long long k = k_al + sidx;
+            fast[u] = sidx + 3 < span && k >= 0;
+            if (fast[u]) raw[u] = load4<KIND>(src, k);
         }
-        t += tstep;
-        if (t >= nco_len) t -= nco_len;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int sidx = s0 + u * sstep;
+            if (fast[u]) {
+                convert4<KIND>(src, raw[u], t, xs + sidx);
+            } else if (sidx < span) {  // history (and the zeros before it), the last samples of the span
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (sidx + i >= span) break;
+                    float r, q;
+                    fetch<KIND>(src, k_al + sidx + i, r, q);
+                    xs[sidx + i] = make_float2(r, q);
+                }
+            }
+            t += tstep;
+            if (t >= nco_len) t -= nco_len;
+        }
     }
 }
 
@@ -295,12 +325,16 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiled
     long long k_hi = a.rel + ((long long)a.ph0 + (j0 + a.I - 1) * a.D) / a.I + (long long)(nq - 1) * a.D;
     const long long k_end = a.rel + ((long long)a.ph0 + (a.nout - 1) * a.D) / a.I;  // newest sample any output needs
     if (k_hi > k_end) k_hi = k_end;  // last tile: never read past the input
-    const long long k_lo = k_first - ((long long)ta.A * a.D - 1);
+    const long long k_lo = k_first - ((long long)AMAX * a.D - 1);  // taps a >= A are zero, their samples just have to exist
     const long long k_al = k_lo - (((k_lo % 4) + 4) % 4);
     const int span = (int)(k_hi - k_al + 1);
-    for (int i = threadIdx.x; i < a.I * a.D * AP; i += blockDim.x) {
-        const int aa = i % AP, pb = i / AP, b = pb % a.D, p = pb / a.D, t = aa * a.D + b;
-        hT[i] = (aa < ta.A && t < a.nt) ? a.bank[(size_t)p * a.nt + t] : 0.0f;
+    for (int pb = threadIdx.x; pb < a.I * a.D; pb += blockDim.x) {  // one (phase, b) row of AP taps per step
+        const int b = pb % a.D, p = pb / a.D;
+#pragma unroll
+        for (int aa = 0; aa < AP; aa++) {
+            const int t = aa * a.D + b;
+            hT[pb * AP + aa] = (aa < ta.A && t < a.nt) ? __ldg(a.bank + (size_t)p * a.nt + t) : 0.0f;
+        }
     }
     stage_span<KIND>(a.src, k_al, span, xs);
     __syncthreads();
@@ -324,9 +358,7 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiled
             cf sv[M + AMAX - 1];  // sv[i] = s_b[i - (AMAX - 1)]
 #pragma unroll
             for (int i = 0; i < M + AMAX - 1; i++) {
-                const int n = i - (AMAX - 1);
-                // taps a >= A are zero, their samples may lie before the staged span: do not touch them
-                const float2 x = (n >= -(ta.A - 1)) ? sp[n * a.D] : make_float2(0.0f, 0.0f);
+                const float2 x = sp[(i - (AMAX - 1)) * a.D];
                 sv[i] = cf{x.x, x.y};
             }
 #pragma unroll
@@ -465,8 +497,14 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
     const int A = (nt + D - 1) / D;
     if (!exact && aligned && A >= 2 && A <= 12 && (size_t)I * D * 12 <= 8192) {
         // register-tiled path: M = 9 outputs per thread, B blocks per phase
-        constexpr int M = 9, kSpanT = 7680;
-        long long B = ((long long)kSpanT - 8 - (long long)(A + 1) * D) / ((long long)M * D);  // span <= (B*M + A + 1)*D + 4
+        constexpr int M = 9, kSpanT = 4096;  // 4 K samples per CTA: six CTAs per SM overlap staging and dot products
+        static const int span_env = [] {  // tuning runs: samples staged per CTA
+            const char *e = getenv("RFA_RS_SPAN");
+            return e && atoi(e) > 0 ? atoi(e) : 0;
+        }();
+        const int span_cap = span_env > 0 && span_env < kSpanT ? span_env : kSpanT;
+        const int amax = A <= 3 ? 3 : (A <= 5 ? 5 : (A <= 9 ? 9 : 12));
+        long long B = ((long long)span_cap - 8 - (long long)(amax + 1) * D) / ((long long)M * D);  // span <= (B*M + amax + 1)*D + 4
         if (B >= 16) B -= B % 16;
         if (B >= 1) {
             ResampleTiledArgs ta{};
@@ -475,12 +513,13 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
             ta.a.tile = (int)((long long)I * M * B);
             ta.B = (int)B;
             ta.A = A;
-            const int amax = A <= 3 ? 3 : (A <= 5 ? 5 : (A <= 9 ? 9 : 12));
             ta.AP = (amax + 3) & ~3;
             const unsigned tgrid = (unsigned)((nout + ta.a.tile - 1) / ta.a.tile);
             long long threads = ((long long)I * B + 31) / 32 * 32;
             if (threads > 256) threads = 256;
-            const size_t tsmem = ((size_t)kSpanT + 8) * sizeof(float2) + (size_t)I * D * ta.AP * sizeof(float);
+            const int span_used = (int)((B * M + amax + 1) * D + 8);
+            ta.a.span_max = span_used;
+            const size_t tsmem = ((size_t)span_used + 8) * sizeof(float2) + (size_t)I * D * ta.AP * sizeof(float);
             static bool tconfigured = false;
             const int mx = (int)(((size_t)kSpanT + 8) * sizeof(float2) + 8192 * sizeof(float));
 #define RFA_RT(KIND, AM)                                                                                           \
