@@ -112,10 +112,15 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
         sim[s] = q;
     }
     __syncthreads();
+    // T = ph0 + j*D decides window (T / I) and phase (T % I): one 64-bit division per CTA, 32-bit ones per output
+    const long long T0 = (long long)a.ph0 + j0 * a.D;
+    const long long q0 = T0 / a.I;
+    const unsigned int r0 = (unsigned int)(T0 % a.I), uI = (unsigned int)a.I, uD = (unsigned int)a.D;
+    const int base = (int)(a.rel + q0 - k_lo);
     for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-        const long long T = (long long)a.ph0 + j * a.D;
-        const int pos = (int)(a.rel + T / a.I - k_lo);  // newest sample of this output's window
-        const float *taps = a.bank + (size_t)(T % a.I) * a.nt;
+        const unsigned int u = r0 + (unsigned int)(j - j0) * uD;  // < I + tile*D < 2^31
+        const int pos = base + (int)(u / uI);  // newest sample of this output's window
+        const float *taps = a.bank + (size_t)(u % uI) * a.nt;
         float ar = 0.0f, ai = 0.0f;
         for (int t = 0; t < a.nt; t++) {  // RationalResampler.kt:124-131, oldest tap last
             const float h = __ldg(taps + t);
@@ -243,7 +248,7 @@ __device__ __forceinline__ void stage_span(const StreamSrc &src, long long k_al,
     }
 }
 
-template <int KIND, bool BANK_SMEM>
+template <int KIND, bool BANK_SMEM, int G>
 __global__ void __launch_bounds__(256) resample_fast_kernel(const ResampleFastArgs fa) {
     const ResampleArgs &a = fa.a;
     extern __shared__ float2 xs[];  // [span_max + 8] samples, then the bank
@@ -262,24 +267,36 @@ __global__ void __launch_bounds__(256) resample_fast_kernel(const ResampleFastAr
         for (int i = threadIdx.x; i < fa.bank_smem; i += blockDim.x) sbank[i] = a.bank[i];
     stage_span<KIND>(a.src, k_al, span, xs);
     __syncthreads();
-    const int G = fa.G, g = threadIdx.x & (G - 1), grp = threadIdx.x / G, ngrp = blockDim.x / G;
+    const int g = threadIdx.x & (G - 1), grp = threadIdx.x / G, ngrp = blockDim.x / G;
+    // T = ph0 + j*D decides window (T / I) and phase (T % I): one 64-bit division per CTA, 32-bit ones per output
+    const long long T0 = (long long)a.ph0 + j0 * a.D;
+    const long long q0 = T0 / a.I;
+    const unsigned int r0 = (unsigned int)(T0 % a.I), uI = (unsigned int)a.I, uD = (unsigned int)a.D;
+    const int base = (int)(a.rel + q0 - k_al);
     for (long long jb = j0; jb < j1; jb += ngrp) {  // warp-uniform trip count (the shuffles below)
         const long long j = jb + grp;
         const bool valid = j < j1;
-        const long long T = (long long)a.ph0 + (valid ? j : j0) * a.D;
-        const int pos = (int)(a.rel + T / a.I - k_al);
-        const size_t tap0 = (size_t)(T % a.I) * a.nt;
+        const unsigned int u = r0 + (valid ? (unsigned int)(j - j0) : 0u) * uD;  // < I + tile*D < 2^31
+        const int pos = base + (int)(u / uI);
+        const size_t tap0 = (size_t)(u % uI) * a.nt;
         const float *taps = BANK_SMEM ? sbank + tap0 : a.bank + tap0;  // two address spaces, two code paths
         const float2 *x = xs + pos;
         cf acc = cf{0.0f, 0.0f}, acc2 = cf{0.0f, 0.0f};
         int t = valid ? g : a.nt;
-        for (; t + G < a.nt; t += 2 * G) {  // two independent chains
-            const float2 x0 = x[-t], x1 = x[-(t + G)];
-            const float h0 = BANK_SMEM ? taps[t] : __ldg(taps + t), h1 = BANK_SMEM ? taps[t + G] : __ldg(taps + t + G);
-            acc = caxpy(h0, cf{x0.x, x0.y}, acc);
-            acc2 = caxpy(h1, cf{x1.x, x1.y}, acc2);
+        for (; t + 3 * G < a.nt; t += 4 * G) {  // four taps per step on two independent chains
+            float2 xv[4];
+            float hv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                xv[k] = x[-(t + k * G)];
+                hv[k] = BANK_SMEM ? taps[t + k * G] : __ldg(taps + t + k * G);
+            }
+            acc = caxpy(hv[0], cf{xv[0].x, xv[0].y}, acc);
+            acc2 = caxpy(hv[1], cf{xv[1].x, xv[1].y}, acc2);
+            acc = caxpy(hv[2], cf{xv[2].x, xv[2].y}, acc);
+            acc2 = caxpy(hv[3], cf{xv[3].x, xv[3].y}, acc2);
         }
-        if (t < a.nt) {
+        for (; t < a.nt; t += G) {
             const float2 x0 = x[-t];
             acc = caxpy(BANK_SMEM ? taps[t] : __ldg(taps + t), cf{x0.x, x0.y}, acc);
         }
@@ -572,36 +589,36 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
         // distance between the windows of neighbouring outputs
         const int G = (tile >= 256 && nout >= 256) ? 1 : 16;
         fa.G = G;
+        // the bank goes to shared memory only when copying it is cheap next to the tile's work
         const size_t bank_floats = (size_t)I * nt;
-        fa.bank_smem = bank_floats * sizeof(float) <= 32 * 1024 ? (int)bank_floats : 0;
+        fa.bank_smem = bank_floats * sizeof(float) <= 4 * 1024 ? (int)bank_floats : 0;
         const size_t fsmem = ((size_t)kSpanMax + 8) * sizeof(float2) + (size_t)fa.bank_smem * sizeof(float);
         static bool fconfigured = false;
-        if (!fconfigured) {
-            const int mx = (int)(((size_t)kSpanMax + 8) * sizeof(float2) + 32 * 1024);
-            cudaFuncSetAttribute(resample_fast_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            cudaFuncSetAttribute(resample_fast_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            cudaFuncSetAttribute(resample_fast_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            cudaFuncSetAttribute(resample_fast_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            cudaFuncSetAttribute(resample_fast_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            cudaFuncSetAttribute(resample_fast_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            cudaFuncSetAttribute(resample_fast_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            cudaFuncSetAttribute(resample_fast_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        const int mx = (int)(((size_t)kSpanMax + 8) * sizeof(float2) + 4 * 1024);
+#define RFA_RF1(KIND, BS, GG)                                                                                          \
+    do {                                                                                                               \
+        if (!fconfigured)                                                                                              \
+            cudaFuncSetAttribute(resample_fast_kernel<KIND, BS, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); \
+        if (launch_now && in.kind == KIND && (fa.bank_smem != 0) == BS && G == GG)                                     \
+            resample_fast_kernel<KIND, BS, GG><<<grid, 256, fsmem, st>>>(fa);                                          \
+    } while (0)
+#define RFA_RF(KIND)                 \
+    do {                             \
+        RFA_RF1(KIND, true, 1);      \
+        RFA_RF1(KIND, true, 16);     \
+        RFA_RF1(KIND, false, 1);     \
+        RFA_RF1(KIND, false, 16);    \
+    } while (0)
+        if (in.kind < 0 || in.kind > 3) return cudaErrorInvalidValue;
+        for (int pass = fconfigured ? 1 : 0; pass < 2; pass++) {
+            const bool launch_now = pass == 1;
+            RFA_RF(0);
+            RFA_RF(1);
+            RFA_RF(2);
+            RFA_RF(3);
             fconfigured = true;
         }
-#define RFA_RF(KIND)                                                                          \
-    do {                                                                                      \
-        if (fa.bank_smem)                                                                     \
-            resample_fast_kernel<KIND, true><<<grid, 256, fsmem, st>>>(fa);                   \
-        else                                                                                  \
-            resample_fast_kernel<KIND, false><<<grid, 256, fsmem, st>>>(fa);                  \
-    } while (0)
-        switch (in.kind) {
-            case 0: RFA_RF(0); break;
-            case 1: RFA_RF(1); break;
-            case 2: RFA_RF(2); break;
-            case 3: RFA_RF(3); break;
-            default: return cudaErrorInvalidValue;
-        }
+#undef RFA_RF1
 #undef RFA_RF
         return cudaGetLastError();
     }
