@@ -228,6 +228,12 @@ int rfa_chain_info(const rfa_chain *chain, int *interpolation, int *decimation, 
 long long rfa_chain_max_audio(const rfa_chain *chain, long long nsamples);
 int rfa_chain_process(rfa_chain *chain, const void *iq, long long nsamples, float *audio, long long capacity,
                       long long *n_audio, int mem);
+/* Time-sharding of a long recording (not in the reference, which runs one sequential
+ * Scheduler/Demodulator pipeline, Scheduler.kt:140-298): put every counter of the chain -- NCO table
+ * index (IQConverter mix index), RationalResampler ctr/delay position, FirFilter.decimationCounter of each
+ * filter -- where a run from sample 0 has it at `sample_index` (a packet boundary), empty the delay
+ * lines, restart FM carry and AGC maximum.  *audio_index = audio samples produced before that point. */
+int rfa_chain_seek(rfa_chain *chain, long long sample_index, long long *audio_index);
 
 /* ---- synthetic IQ (benchmark / test input; the reference ships no input fixtures) ------ */
 /* All-integer generator of SURVEY.md 8(d): sample n depends on n alone, so any segment of a

@@ -102,6 +102,7 @@ SIGNATURES = {
     "rfa_chain_info": (_i, [_vp, _pi, _pi, _pi, _pi, _pi, _pi, _pi]),
     "rfa_chain_max_audio": (_ll, [_vp, _ll]),
     "rfa_chain_process": (_i, [_vp, _vp, _ll, _vp, _ll, _pll, _i]),
+    "rfa_chain_seek": (_i, [_vp, _ll, _pll]),
     "rfa_synth_iq": (_i, [_vp, _i, C.c_uint32, C.POINTER(SynthComp), _i, _i, _ll, _ll, _vp, _i]),
 }
 

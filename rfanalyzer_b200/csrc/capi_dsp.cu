@@ -570,6 +570,63 @@ long long rfa_chain_max_audio(const rfa_chain *ch, long long nsamples) {
     return (long long)((double)nsamples * kAudioRate / ch->d.sample_rate) + 64;
 }
 
+// Position a chain at input sample `sample_index` of a recording: every counter (NCO phase, resampler
+// phase, the decimation counters of the filters behind it) takes the value a sequential run from
+// sample 0 would have there, every delay line is emptied, the FM carry and the AGC maximum restart.
+// A rank of a time-sharded run seeks to a packet boundary one warm-up halo before its segment,
+// processes the halo (which refills the delay lines with real samples) and discards its audio.
+// *audio_index = number of audio samples the sequential run has produced before sample_index.
+int rfa_chain_seek(rfa_chain *ch, long long sample_index, long long *audio_index) {
+    RFA_REQUIRE(ch != nullptr, "rfa_chain_seek: NULL");
+    RFA_REQUIRE(sample_index >= 0 && sample_index % ch->d.packet_samples == 0,
+                "seek position %lld is not a packet boundary (%d samples)", sample_index, ch->d.packet_samples);
+    rfa_ctx *c = ch->ctx;
+    if (int rc = c->use()) return rc;
+    rfa_fir *firs[4] = {ch->user, ch->band, ch->audio1, ch->audio2};
+    for (rfa_fir *f : firs)
+        if (f) {
+            f->first = f->initial_first();
+            if (int rc = f->h.reset(c)) return rc;
+        }
+    ch->rs->rel = 0;
+    ch->rs->ph = 0;
+    if (int rc = ch->rs->h.reset(c)) return rc;
+    RFA_CK(cudaMemsetAsync(ch->fm_carry.p, 0, 2 * sizeof(float), c->stream));
+    RFA_CK(cudaMemsetAsync(ch->agc_state.p, 0, sizeof(float), c->stream));
+    // counters: the same arithmetic rfa_chain_process applies, for sample_index inputs in one step
+    const long long n = sample_index;
+    ch->nco_idx = (int)(n % ch->nco_len);
+    long long produced = 0;
+    if (n > 0) {
+        rfa_resampler *r = ch->rs;
+        const long long nq = r->count(n);
+        const long long T = (long long)r->ph + nq * r->D, kk = r->rel + T / r->I;
+        r->rel = kk - n;
+        r->ph = (int)(T % r->I);
+        auto advance = [](rfa_fir *f, long long nin) {
+            const long long nout = f->count(nin);
+            f->first = f->first + nout * f->dec - nin;
+            return nout;
+        };
+        long long ndem = advance(ch->user, nq);
+        int dem_rate = ch->quad_rate;
+        if (ch->band) {
+            ndem = advance(ch->band, ndem);
+            dem_rate = ch->quad_rate / ch->band->dec;
+        }
+        produced = ndem;
+        if (dem_rate > kAudioRate) {
+            const int ratio = dem_rate / kAudioRate;
+            if (ratio == 8 || ratio == 2) {
+                produced = advance(ch->audio1, ndem);
+                if (ratio == 8) produced = advance(ch->audio2, produced);
+            }
+        }
+    }
+    if (audio_index) *audio_index = produced;
+    return RFA_OK;
+}
+
 int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *audio, long long capacity,
                       long long *n_audio, int mem) {
     RFA_REQUIRE(ch && n_audio, "rfa_chain_process: NULL argument");

@@ -575,6 +575,13 @@ class ChainPlan:
     def max_audio(self, nsamples):
         return self.ctx.lib.rfa_chain_max_audio(self.handle, int(nsamples))
 
+    def seek(self, sample_index):
+        """Position the chain at a packet boundary of the recording (rfa_chain_seek); returns the number
+        of audio samples a sequential run has produced before that point."""
+        n = C.c_longlong()
+        check(self.ctx.lib.rfa_chain_seek(self.handle, int(sample_index), C.byref(n)))
+        return n.value
+
     def process(self, iq, nsamples, audio):
         """audio: float32 buffer of at least max_audio(nsamples); returns the number of samples written."""
         n = C.c_longlong()

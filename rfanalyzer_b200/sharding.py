@@ -91,3 +91,68 @@ class ShardedSpectrum:
         dist.all_gather(gathered, mine, group=self.group)
         tail = assemble_tail(gathered, total_frames, self.world, self.L).contiguous()
         self.plan.ctx.average_rows(tail, 0, 1, 0, self.n, min(self.L + 1, total_frames), self.L, self.n, avg)
+
+
+# ---------------------------------------------------------------------------------------------
+# IQ -> audio chain (demodulation path)
+# ---------------------------------------------------------------------------------------------
+def shard_packets(total_samples, packet_samples, world_size, rank):
+    """Contiguous run of whole packets for rank `rank`: (first_sample, nsamples).  Packetisation is part of
+    the reference's semantics (per-packet mean and AGC, Demodulator.kt:293-302), so segments start on
+    packet boundaries; only the recording's last packet may be short."""
+    npk = -(-int(total_samples) // int(packet_samples))
+    first_pk, n_pk = shard_frames(npk, world_size, rank)
+    first = first_pk * packet_samples
+    end = min((first_pk + n_pk) * packet_samples, int(total_samples))
+    return first, max(0, end - first)
+
+
+def default_halo_packets(mode):
+    """Warm-up packets re-processed before a segment.  The delay lines (resampler, user / band-pass /
+    audio filters) and the FM carry are exact after ONE packet; the AGC maximum of AM / SSB / CW decays by
+    0.95 per packet (Demodulator.kt:290), so its memory of what came before the halo is 0.95^256 = 2e-6."""
+    return 1 if mode in (2, 3) else 256  # MODE_NFM, MODE_WFM
+
+
+class ShardedChain:
+    """One rank's share of a time-sharded demodulation run: seek to a packet boundary one halo before the
+    segment, re-process the halo (audio discarded), then the segment.  No collective on the data path: the
+    audio of rank r simply follows the audio of rank r-1; `gather_layout` tells every rank where each piece
+    goes."""
+
+    def __init__(self, plan, rank=0, world_size=1, halo_packets=None, group=None):
+        self.plan, self.rank, self.world, self.group = plan, rank, world_size, group
+        self.packet = plan.desc.packet_samples
+        self.halo_packets = default_halo_packets(plan.desc.mode) if halo_packets is None else int(halo_packets)
+
+    def segment(self, total_samples, rank=None):
+        """(halo_start, first, nsamples): the rank needs input samples [halo_start, first + nsamples)."""
+        first, n = shard_packets(total_samples, self.packet, self.world, self.rank if rank is None else rank)
+        halo_start = max(0, first - self.halo_packets * self.packet)
+        return halo_start, first, n
+
+    def process(self, iq_from_halo, total_samples, audio):
+        """iq_from_halo: raw IQ of this rank starting at its halo_start.  Writes the segment's audio to
+        `audio` and returns (audio_index, n_audio): where it sits in the whole recording's audio."""
+        halo_start, first, n = self.segment(total_samples)
+        bps = 4 if self.plan.desc.format == 2 else 2
+        index = self.plan.seek(halo_start)
+        nh = first - halo_start
+        if nh:
+            cap = audio.numel() if hasattr(audio, "numel") else len(audio)
+            if cap < self.plan.max_audio(nh):
+                raise ValueError("audio buffer smaller than the halo's audio: give it max_audio(max(halo, segment))")
+            index += self.plan.process(iq_from_halo[: nh * bps], nh, audio)  # overwritten by the segment's audio
+        got = self.plan.process(iq_from_halo[nh * bps:(nh + n) * bps], n, audio) if n else 0
+        return index, got
+
+    def gather_layout(self, index, count):
+        """all_gather of every rank's (audio_index, n_audio)."""
+        if self.world == 1:
+            return [(index, count)]
+        mine = torch.tensor([index, count], dtype=torch.int64)
+        if dist.get_backend(self.group) == "nccl":
+            mine = mine.cuda()
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=self.group)
+        return [(int(t[0]), int(t[1])) for t in out]

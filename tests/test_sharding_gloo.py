@@ -72,3 +72,78 @@ def test_two_rank_reduction_over_gloo(total_frames, L):
     for _, peaks, tail in results:
         assert np.array_equal(peaks, rows_all.max(axis=0))
         assert np.array_equal(tail, want_tail)
+
+
+# ---- demodulation chain: packet-aligned segments with a warm-up halo ---------------------------------
+from rfanalyzer_b200.sharding import ShardedChain, default_halo_packets, shard_packets
+
+
+def test_shard_packets_cover_the_recording_on_packet_boundaries():
+    for total, packet in ((0, 8192), (1, 8192), (8192 * 7, 8192), (8192 * 7 + 5, 8192), (65536 * 33 - 1, 65536)):
+        for world in (1, 2, 3, 8):
+            segs = [shard_packets(total, packet, world, r) for r in range(world)]
+            assert segs[0][0] == 0 and sum(n for _, n in segs) == total
+            for (a, n), (b, m) in zip(segs, segs[1:]):
+                assert a + n == b or m == 0
+                assert b % packet == 0 or m == 0
+
+
+class _FakePlan:
+    """Counts what ShardedChain asks of a chain plan: 1 audio sample per 50 input samples."""
+    class desc:
+        packet_samples, mode, format = 1000, 3, 1
+
+    def __init__(self):
+        self.calls, self.pos = [], 0
+
+    def seek(self, n):
+        self.pos = n
+        self.calls.append(("seek", n))
+        return n // 50
+
+    def max_audio(self, n):
+        return n // 50 + 64
+
+    def process(self, iq, n, audio):
+        assert len(iq) == 2 * n
+        self.calls.append(("process", self.pos, n))
+        self.pos += n
+        return n // 50
+
+
+def _chain_worker(rank, world, port, total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = _FakePlan()
+    sc = ShardedChain(plan, rank, world, halo_packets=2)
+    halo_start, first, n = sc.segment(total)
+    iq = np.zeros(2 * (first + n - halo_start), np.uint8)
+    audio = np.zeros(plan.max_audio(max(first - halo_start, n)), np.float32)
+    index, got = sc.process(iq, total, audio)
+    layout = sc.gather_layout(index, got)
+    q.put((rank, plan.calls, layout))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_chain_layout_over_gloo():
+    world, total = 2, 1000 * 9 + 400
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chain_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+    (r0, calls0, lay0), (r1, calls1, lay1) = res
+    assert lay0 == lay1                                   # every rank knows every piece
+    assert lay0[0][0] == 0 and lay0[0][0] + lay0[0][1] == lay0[1][0]   # contiguous audio
+    assert lay0[1][0] + lay0[1][1] == total // 50
+    assert calls0 == [("seek", 0), ("process", 0, 5000)]  # rank 0: no halo
+    assert calls1 == [("seek", 3000), ("process", 3000, 2000), ("process", 5000, 4400)]
+    assert default_halo_packets(3) == 1 and default_halo_packets(1) == 256
