@@ -428,7 +428,7 @@ int rfa_spectrum_plan_create(rfa_ctx *c, const rfa_spectrum_desc *d, rfa_spectru
     pl->d = *d;
     const int n = d->fft_size, nl = n > 16384 ? 16384 : n;
     int rc = c->get_twiddles(nl, &pl->tw);
-    if (!rc && n > 16384) rc = c->get_twiddles(-n, &pl->twN);
+    if (!rc && (n > 16384 || n == 4096)) rc = c->get_twiddles(-n, &pl->twN);  // 4096: the 64 x 64 kernel's table
     if (!rc) rc = c->get_window(d->window, n, &pl->win);
     if (!rc) rc = pl->ticket.ensure(TICKET_WORDS * sizeof(unsigned int));
     if (!rc && cudaMemsetAsync(pl->ticket.p, 0, TICKET_WORDS * sizeof(unsigned int), c->stream) != cudaSuccess) rc = RFA_ERR_CUDA;

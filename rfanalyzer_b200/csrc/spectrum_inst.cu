@@ -4,6 +4,7 @@
 
 #include "spectrum_launch.h"
 #include "spectrum2_kernel.cuh"
+#include "spectrum64_kernel.cuh"
 
 namespace rfa {
 namespace {
@@ -82,6 +83,28 @@ cudaError_t launch_two(const SpectrumLaunch &L, bool query, int *grid_out, int *
     return cudaGetLastError();
 }
 
+// two-pass 64 x 64 kernel for N = 4096 (spectrum64_kernel.cuh, experiment: RFA_K64=1, no time average)
+template <int IN>
+cudaError_t launch_64(const SpectrumLaunch &L) {
+    using G = Geom64;
+    auto kern = spectrum64_kernel<IN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+        if (err != cudaSuccess) return err;
+        configured = true;
+    }
+    long long need = (L.p.nframes + G::SLOTS - 1) / G::SLOTS;
+    long long grid = need < L.num_sms ? need : L.num_sms;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, G::CTA, G::SMEM, L.stream>>>(L.p);
+    return cudaGetLastError();
+}
+static bool k64_enabled() {
+    const char *e = getenv("RFA_K64");
+    return e && atoi(e) == 1;
+}
+
 // RFA_DUAL=1 selects the dual-frame kernel for N = 256 .. 4096 (read at every launch so that tests
 // and timing runs can switch).  Default: the single-frame kernel, which is ahead on B200 for now
 // (gpurun_out/timing17.log: 45.5 us vs 47.5 us per 2^24 samples at N = 4096).
@@ -92,6 +115,15 @@ static bool dual_enabled() {
 
 template <int NL, int S>
 cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc) {
+    if constexpr (S == 1 && NL == 4096) {
+        if (L.out_kind == OUT_DB && !query && k64_enabled() && L.p.avg == nullptr && L.p.twN != nullptr) {
+            switch (L.in_fmt) {
+                case FMT_S8: return launch_64<FMT_S8>(L);
+                case FMT_U8: return launch_64<FMT_U8>(L);
+                case FMT_S16LE: return launch_64<FMT_S16LE>(L);
+            }
+        }
+    }
     if constexpr (S == 1 && NL >= 256 && NL <= 4096) {
         if (L.out_kind == OUT_DB && dual_enabled()) {
             switch (L.in_fmt) {

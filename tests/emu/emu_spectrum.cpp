@@ -12,6 +12,7 @@
 #include "../../rfanalyzer_b200/csrc/rfa_tables.h"
 #include "../../rfanalyzer_b200/csrc/spectrum_kernel.cuh"
 #include "../../rfanalyzer_b200/csrc/spectrum2_kernel.cuh"
+#include "../../rfanalyzer_b200/csrc/spectrum64_kernel.cuh"
 
 using namespace rfa;
 
@@ -196,6 +197,41 @@ static int emu_dispatch(int N, int in_fmt, int out_kind, int window_kind, const 
 extern "C" int emu_spectrum_avg(int N, int in_fmt, int out_kind, int window_kind /* -1: none */, const void *in,
                                 const float *in_im, long long nframes, float *rows, float *peaks, float *avg, int L) {
     return emu_dispatch(N, in_fmt, out_kind, window_kind, in, in_im, nframes, rows, peaks, avg, L, false, 0);
+}
+
+// ---- two-pass 64 x 64 kernel (spectrum64_kernel.cuh), N = 4096 ----
+template <int IN>
+int emu_k64(const void *in, int window_kind, long long nframes, float *rows, float *peaks) {
+    using F = SpectrumFrame64<IN>;
+    constexpr int N = 4096, ROW = Geom64::ROW;
+    std::vector<cf> twN(N), tw(64 * 64), x(64 * ROW);
+    make_twiddles(N, twN.data());
+    for (int i = 0; i < 64 * 64; i++) tw[i] = twN[((i >> 6) * (i & 63)) & 4095];
+    std::vector<float> w(N, unit_scale<IN>());
+    if (window_kind >= 0) {
+        make_window(window_kind, N, w.data());
+        for (auto &v : w) v *= unit_scale<IN>();
+    }
+    std::vector<std::array<float, 64>> PK(64);
+    for (auto &a : PK) a.fill(-999999.0f);
+    const float bias = -3.0102999566398120f * log2f((float)N);
+    for (long long f = 0; f < nframes; f++) {
+        for (int t = 0; t < 64; t++)
+            F::pass_a((const char *)in + (f * (long long)N + t) * in_elem_bytes<IN>(), w.data() + t, tw.data() + t, x.data() + t);
+        for (int t = 0; t < 64; t++) F::template pass_b<true, true>(x.data() + t * ROW, rows + f * N + t, PK[t].data(), bias);
+    }
+    for (int t = 0; t < 64; t++)
+        for (int c = 0; c < 64; c++) peaks[F::peak_index(t, c)] = PK[t][c];
+    return 0;
+}
+
+extern "C" int emu_spectrum64(int in_fmt, int window_kind, const void *in, long long nframes, float *rows, float *peaks) {
+    switch (in_fmt) {
+        case FMT_S8: return emu_k64<FMT_S8>(in, window_kind, nframes, rows, peaks);
+        case FMT_U8: return emu_k64<FMT_U8>(in, window_kind, nframes, rows, peaks);
+        case FMT_S16LE: return emu_k64<FMT_S16LE>(in, window_kind, nframes, rows, peaks);
+    }
+    return -1;
 }
 
 // the dual-frame kernel's path (N = 256 .. 4096, integer formats, dB rows)

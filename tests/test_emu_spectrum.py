@@ -116,3 +116,18 @@ def test_dual_frame_store_from(emu, oracle):
     r, p, _ = oracle.spectrum_run(1, iq, n, 1)
     assert np.all(rows[:2] == 7.0)
     assert np.abs(rows[2:] - r[2:]).max() < 0.01 and np.abs(peaks - p).max() < 0.01
+
+
+# ---- two-pass 64 x 64 kernel (spectrum64_kernel.cuh), N = 4096 ----
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_k64_path_vs_oracle(emu, oracle, fmt):
+    n, frames = 4096, 3
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows = np.zeros((frames, n), np.float32)
+    peaks = np.zeros(n, np.float32)
+    assert emu.emu_spectrum64(fmt, 0, iq.ctypes.data, frames, rows.ctypes.data, peaks.ctypes.data) == 0
+    r, p, _ = oracle.spectrum_run(fmt, iq, n, 0)
+    assert np.abs(rows - r).max() < 0.01
+    assert np.abs(peaks - p).max() < 0.01
+    lin, lin_ref = 10.0 ** (rows / 5.0), 10.0 ** (r / 5.0)
+    assert np.all(np.abs(lin - lin_ref) <= 1e-4 * lin_ref + 1e-6 * lin_ref.max())

@@ -292,3 +292,24 @@ def test_dual_frame_kernel_ring_and_history(gpu_ctx, oracle, monkeypatch):
             L_o.orc_time_average(proc, L, avg_ref)
             assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
     L_o.orc_fftproc_free(proc)
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_two_pass_64x64_kernel_vs_oracle(gpu_ctx, oracle, monkeypatch, fmt):
+    """spectrum64_kernel (RFA_K64=1, N = 4096, no time average): 64 points per thread, one exchange."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    monkeypatch.setenv("RFA_K64", "1")
+    n, frames = 4096, 601
+    iq = oracle.synth_iq(fmt, n * frames)
+    r, p, _ = oracle.spectrum_run(fmt, iq, n, 0)
+    plan = rfa.SpectrumPlan(gpu_ctx, fmt, n, avg_len=0)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        rows = torch.zeros((frames, n), dtype=torch.float32, device="cuda")
+        peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        plan.process(torch.from_numpy(iq).cuda(), frames, rows=rows, peaks=peaks)
+        gpu_ctx.sync()
+    rows, peaks = rows.cpu().numpy(), peaks.cpu().numpy()
+    assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL
+    assert lin_ok(rows, r)
+    assert np.array_equal(peaks, rows.max(axis=0))
