@@ -153,6 +153,33 @@ int rfa_channel_strength(rfa_ctx *ctx, const float *rows, long long row0, long l
                          int bin_end, float *out, int mem_out);
 /* FftProcessor.kt:199-217: shift `nrows` device rows by `shift` bins, fill with -9999f. */
 int rfa_shift_rows(rfa_ctx *ctx, float *rows, long long nrows, long long row_stride, int n, int shift);
+
+/* ---- waterfall / FFT-trace preprocessing -------------------------------------
+ * AnalyzerSurface.drawPreprocessing (ui/AnalyzerSurface.kt:646-734), arithmetic only: per pixel the mean of
+ * the row's bins (:703-713), colour-map index int((avg-minDB)*mapSize/(maxDB-minDB)) clamped (:726-727),
+ * black outside the frame (:728-731), the FFT trace = mean over the newest avg_len+1 rows of those means
+ * (:716-719), the peak trace y coordinates (:714).  Bit-identical to the JVM (same float32 order).
+ * `rows` is the device-resident ring the spectrum plan fills (newest_row = FftProcessorData.readIndex), so a
+ * display client reads back `width` pixels per row instead of fft_size floats. */
+typedef struct {
+    int fft_size;                 /* bins per row */
+    long long frequency;          /* FftProcessorData.frequency of the rows */
+    int sample_rate;              /* FftProcessorData.sampleRate */
+    long long viewport_frequency, viewport_sample_rate;
+    int width, fft_height;        /* pixels */
+    float min_db, max_db;         /* viewportVerticalScale */
+    int avg_len;                  /* fftAverageLength */
+    int ring_rows;                /* waterfallBuffer.size */
+    long long row_stride;         /* floats between rows, 0 = fft_size */
+    int newest_row;               /* ring index of the newest row (currentRowIdx) */
+    int first_row, nrows;         /* rowNumber range to render, 0 = newest (dirty rows only, :688-691) */
+} rfa_render_desc;
+/* argb / color_index: [ring_rows][width] indexed by ring row like colorBuffer (color_index = -1 outside the
+ * frame); time_average / peaks_y: [width] (time_average needs first_row = 0 and nrows > avg_len; NaN outside
+ * the frame).  Any output may be NULL.  out_mem says where the outputs live, colormap_mem where the map lives. */
+int rfa_render_waterfall(rfa_ctx *ctx, const rfa_render_desc *desc, const float *rows, const float *peaks,
+                         const uint32_t *colormap, int colormap_size, int colormap_mem, uint32_t *argb,
+                         int *color_index, float *time_average, float *peaks_y, int out_mem);
 int rfa_fill(rfa_ctx *ctx, float *dst, long long count, float value);
 
 /* ---- filter design (host functions; float/double usage follows the reference) ---------- */

@@ -37,6 +37,14 @@ class SpectrumOut(C.Structure):
                 ("peaks", C.c_void_p), ("peaks_accumulate", C.c_int), ("avg", C.c_void_p)]
 
 
+class RenderDesc(C.Structure):
+    _fields_ = [("fft_size", C.c_int), ("frequency", C.c_longlong), ("sample_rate", C.c_int),
+                ("viewport_frequency", C.c_longlong), ("viewport_sample_rate", C.c_longlong),
+                ("width", C.c_int), ("fft_height", C.c_int), ("min_db", C.c_float), ("max_db", C.c_float),
+                ("avg_len", C.c_int), ("ring_rows", C.c_int), ("row_stride", C.c_longlong),
+                ("newest_row", C.c_int), ("first_row", C.c_int), ("nrows", C.c_int)]
+
+
 class SynthComp(C.Structure):
     _fields_ = [("step", C.c_uint32), ("amp", C.c_int32), ("mod_step", C.c_uint32), ("mod_k", C.c_int32)]
 
@@ -97,6 +105,7 @@ SIGNATURES = {
     "rfa_demod_am": (_i, [_vp, _vp, _vp, _ll, _vp, _f, _vp, _i, _i]),
     "rfa_agc": (_i, [_vp, _vp, _ll, _vp, _f, _i, _i]),
     "rfa_mode_info": (_i, [_i, _pi, _pi, _pi, _pi]),
+    "rfa_render_waterfall": (_i, [_vp, C.POINTER(RenderDesc), _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "rfa_chain_create": (_i, [_vp, C.POINTER(ChainDesc), _pvp]),
     "rfa_chain_destroy": (_i, [_vp]),
     "rfa_chain_info": (_i, [_vp, _pi, _pi, _pi, _pi, _pi, _pi, _pi]),

@@ -621,6 +621,107 @@ int rfa_channel_bins(int n, long long frequency, int sample_rate, long long chan
     return RFA_OK;
 }
 
+// Java's (int) cast of a double: NaN -> 0, saturating
+static int java_int(double v) {
+    if (v != v) return 0;
+    if (v >= 2147483647.0) return 2147483647;
+    if (v <= -2147483648.0) return -2147483647 - 1;
+    return (int)v;
+}
+
+int rfa_render_waterfall(rfa_ctx *c, const rfa_render_desc *d, const float *rows, const float *peaks,
+                         const uint32_t *colormap, int colormap_size, int colormap_mem, uint32_t *argb,
+                         int *color_index, float *time_average, float *peaks_y, int out_mem) {
+    RFA_REQUIRE(c && d && rows, "rfa_render_waterfall: NULL argument");
+    RFA_REQUIRE(d->fft_size > 0 && d->sample_rate > 0 && d->width > 0 && d->ring_rows > 0, "bad render geometry");
+    RFA_REQUIRE(d->first_row >= 0 && d->nrows >= 0 && d->first_row + d->nrows <= d->ring_rows,
+                "row range %d+%d outside the ring of %d rows", d->first_row, d->nrows, d->ring_rows);
+    RFA_REQUIRE(d->avg_len >= 0 && d->avg_len <= 30, "avg_len %d outside 0..30", d->avg_len);
+    RFA_REQUIRE(colormap_size > 0 && (colormap || !argb), "a colour map is needed for ARGB output");
+    RFA_REQUIRE(!time_average || (d->first_row == 0 && d->nrows > d->avg_len),
+                "the FFT trace needs the newest avg_len+1 rows in the rendered range");
+    if (d->nrows == 0) return RFA_OK;
+    if (int rc = c->use()) return rc;
+    // viewport arithmetic, AnalyzerSurface.kt:647-676 (Float / Double exactly as written there)
+    const int fftSize = d->fft_size, width = d->width;
+    const float samplesPerHz = (float)fftSize / (float)d->sample_rate;
+    const long long frequencyDiff = d->viewport_frequency - d->frequency;
+    const long long sampleRateDiff = d->viewport_sample_rate - (long long)d->sample_rate;
+    const int start = java_int(((double)frequencyDiff - sampleRateDiff / 2.0) * samplesPerHz);
+    const int end = fftSize + java_int(((double)frequencyDiff + sampleRateDiff / 2.0) * samplesPerHz);
+    const float samplesPerPx = (float)(end - start) / (float)width;
+    const float dbDiff = d->max_db - d->min_db;
+    RenderDesc r;
+    r.rows = rows;
+    r.row_stride = d->row_stride > 0 ? d->row_stride : fftSize;
+    r.ring_rows = d->ring_rows;
+    r.n = fftSize;
+    r.newest = d->newest_row;
+    r.first_row = d->first_row;
+    r.nrows = d->nrows;
+    r.peaks = peaks;
+    r.width = width;
+    r.start = start;
+    r.samples_per_px = samplesPerPx;
+    r.first_pixel = start >= 0 ? 0 : java_int((double)((float)(start * -1) / samplesPerPx));
+    r.last_pixel = end >= fftSize ? java_int((double)((float)(fftSize - start) / samplesPerPx))
+                                  : java_int((double)((float)(end - start) / samplesPerPx));
+    r.min_db = d->min_db;
+    r.db_width = (float)d->fft_height / dbDiff;
+    r.scale = (float)colormap_size / dbDiff;
+    r.fft_height = (float)d->fft_height;
+    r.colormap_size = colormap_size;
+    r.avg_len = d->avg_len;
+    if (colormap) {
+        if (colormap_mem == RFA_MEM_HOST) {
+            if (int rc = c->render[0].ensure((size_t)colormap_size * sizeof(uint32_t))) return rc;
+            RFA_CK(cudaMemcpyAsync(c->render[0].p, colormap, (size_t)colormap_size * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, c->stream));
+            r.colormap = c->render[0].as<uint32_t>();
+        } else {
+            r.colormap = colormap;
+        }
+    }
+    const size_t px = (size_t)d->ring_rows * width;
+    const bool host = out_mem == RFA_MEM_HOST;
+    if (time_average) {
+        if (int rc = c->render[1].ensure((size_t)(d->avg_len + 1) * width * sizeof(float))) return rc;
+        r.row_means = c->render[1].as<float>();
+    }
+    auto out_buf = [&](int slot, void *user, size_t bytes, void **dev) -> int {
+        *dev = user;
+        if (user && host) {
+            if (int rc = c->render[slot].ensure(bytes)) return rc;
+            *dev = c->render[slot].p;
+        }
+        return RFA_OK;
+    };
+    void *dv;
+    if (int rc = out_buf(2, argb, px * sizeof(uint32_t), &dv)) return rc;
+    r.argb = (uint32_t *)dv;
+    if (int rc = out_buf(3, color_index, px * sizeof(int), &dv)) return rc;
+    r.color_index = (int *)dv;
+    if (int rc = out_buf(4, time_average, (size_t)width * sizeof(float), &dv)) return rc;
+    r.time_average = (float *)dv;
+    if (int rc = out_buf(5, peaks_y, (size_t)width * sizeof(float), &dv)) return rc;
+    r.peaks_y = (float *)dv;
+    if (host) {  // rows outside the rendered range keep what the caller has: bring them along
+        if (argb) RFA_CK(cudaMemcpyAsync(r.argb, argb, px * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        if (color_index) RFA_CK(cudaMemcpyAsync(r.color_index, color_index, px * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    cudaError_t e = render_launch(r, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "render kernels");
+    c->launches += time_average ? 2 : 1;
+    if (host) {
+        if (argb) RFA_CK(cudaMemcpyAsync(argb, r.argb, px * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (color_index) RFA_CK(cudaMemcpyAsync(color_index, r.color_index, px * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (time_average) RFA_CK(cudaMemcpyAsync(time_average, r.time_average, (size_t)width * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (peaks_y) RFA_CK(cudaMemcpyAsync(peaks_y, r.peaks_y, (size_t)width * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    }
+    return RFA_OK;
+}
+
 int rfa_channel_strength(rfa_ctx *c, const float *rows, long long row0, long long row_step, long long ring_rows,
                          long long row_stride, long long nrows, int bin_start, int bin_end, float *out,
                          int mem_out) {

@@ -60,6 +60,7 @@ struct rfa_ctx {
     std::map<std::pair<int, int>, float *> windows;   // per (kind, size)
     short *synth_table = nullptr;                     // generator's cosine table
     rfa::Buf stage[8];                                // staging for RFA_MEM_HOST calls
+    rfa::Buf render[6];                               // rfa_render_waterfall: colour map, row means, host-mode outputs
     int get_twiddles(int n, const rfa::cf **out);
     int get_window(int kind, int n, const float **out);
     int use();  // cudaSetDevice

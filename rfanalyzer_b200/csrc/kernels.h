@@ -1,5 +1,6 @@
 // kernels.h -- launchers of the non-spectrum kernels (convert.cu, fir.cu, demod.cu).
 #pragma once
+#include <stdint.h>
 #include <cuda_runtime.h>
 
 namespace rfa {
@@ -32,6 +33,26 @@ cudaError_t demod_power_launch(const float *re, const float *im, long long n, fl
                                cudaStream_t st);
 cudaError_t agc_launch(float *x, const long long *off, int npackets, long long max_packet, bool subtract_mean,
                        float *state, float *scratch, float volume, bool exact, int num_sms, cudaStream_t st);
+
+// waterfall / trace preprocessing (render.cu); viewport scalars are computed by the caller (capi.cu)
+struct RenderDesc {
+    const float *rows = nullptr;
+    long long row_stride = 0;
+    int ring_rows = 0, n = 0, newest = 0, first_row = 0, nrows = 0;
+    const float *peaks = nullptr;
+    int width = 0, start = 0;
+    float samples_per_px = 0;
+    int first_pixel = 0, last_pixel = 0;
+    float min_db = 0, scale = 0, db_width = 0, fft_height = 0;
+    const uint32_t *colormap = nullptr;
+    int colormap_size = 0;
+    uint32_t black = 0xFF000000u;
+    int avg_len = 0;
+    uint32_t *argb = nullptr;
+    int *color_index = nullptr;
+    float *row_means = nullptr, *peaks_y = nullptr, *time_average = nullptr;
+};
+cudaError_t render_launch(const RenderDesc &d, cudaStream_t st);
 
 struct SynthComp {
     unsigned int step;

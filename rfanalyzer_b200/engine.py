@@ -113,6 +113,23 @@ class Context:
     def shift_rows(self, rows, nrows, row_stride, n, shift):
         check(self.lib.rfa_shift_rows(self.handle, ptr(rows), int(nrows), int(row_stride), int(n), int(shift)))
 
+    def render_waterfall(self, rows, peaks, n, frequency, sample_rate, viewport_frequency, viewport_sample_rate,
+                         width, fft_height, min_db, max_db, avg_len, ring_rows, newest_row, colormap=None,
+                         colormap_size=None, argb=None, color_index=None, time_average=None, peaks_y=None,
+                         first_row=0, nrows=None, row_stride=0):
+        """AnalyzerSurface.drawPreprocessing on the device ring `rows` (rfa_render_waterfall).  Outputs are
+        host arrays or device tensors, all of one kind."""
+        d = _lib.RenderDesc(int(n), int(frequency), int(sample_rate), int(viewport_frequency),
+                            int(viewport_sample_rate), int(width), int(fft_height), float(min_db), float(max_db),
+                            int(avg_len), int(ring_rows), int(row_stride), int(newest_row), int(first_row),
+                            int(ring_rows - first_row if nrows is None else nrows))
+        outs = [o for o in (argb, color_index, time_average, peaks_y) if o is not None]
+        size = colormap_size if colormap_size is not None else (len(colormap) if colormap is not None else 0)
+        check(self.lib.rfa_render_waterfall(self.handle, C.byref(d), ptr(rows), ptr(peaks), ptr(colormap), int(size),
+                                            _mem_of(colormap) if colormap is not None else _lib.MEM_HOST,
+                                            ptr(argb), ptr(color_index), ptr(time_average), ptr(peaks_y),
+                                            _mem_of(*outs) if outs else _lib.MEM_HOST))
+
     def fill(self, dst, count, value):
         check(self.lib.rfa_fill(self.handle, ptr(dst), int(count), float(value)))
 
