@@ -132,6 +132,7 @@ typedef struct {
 
 int rfa_spectrum_plan_create(rfa_ctx *ctx, const rfa_spectrum_desc *desc, rfa_spectrum_plan **out);
 int rfa_spectrum_plan_destroy(rfa_spectrum_plan *plan);
+int rfa_spectrum_plan_info(const rfa_spectrum_plan *plan, int *fft_size, int *format, int *avg_len);
 /* iq: nframes * fft_size samples, frames contiguous and non-overlapping (Scheduler.kt:254-276). */
 int rfa_spectrum_process(rfa_spectrum_plan *plan, const void *iq, long long nframes,
                          const rfa_spectrum_out *out, int mem);
@@ -261,6 +262,43 @@ int rfa_chain_process(rfa_chain *chain, const void *iq, long long nsamples, floa
  * filter -- where a run from sample 0 has it at `sample_index` (a packet boundary), empty the delay
  * lines, restart FM carry and AGC maximum.  *audio_index = audio samples produced before that point. */
 int rfa_chain_seek(rfa_chain *chain, long long sample_index, long long *audio_index);
+
+/* ---- IQ recordings on disk -------------------------------------------------------
+ * IQ_FILE_FORMAT.md: header-less interleaved IQ; the metadata lives in the file NAME
+ * "{yyyyMMdd-HHmmss}_{name}_{HACKRF|RTLSDR|AIRSPY|HYDRASDR}_{frequency}_{sampleRate}.iq" (RecordingDao.kt:87-90). */
+enum { RFA_FILE_HACKRF = 0, RFA_FILE_RTLSDR = 1, RFA_FILE_AIRSPY = 2, RFA_FILE_HYDRASDR = 3 }; /* FilesourceFileFormat */
+typedef struct {
+    int file_format;       /* RFA_FILE_* */
+    long long frequency;   /* Hz */
+    long long sample_rate; /* samples/s */
+    int have_format, have_frequency, have_sample_rate; /* set when the name carried the field */
+} rfa_recording_info;
+/* MainViewModel.setFilesourceUri (ui/MainViewModel.kt:2034-2080): fields the name does not carry keep the values
+ * `info` came in with, exactly as the app keeps its current settings. */
+int rfa_recording_parse_name(const char *filename, rfa_recording_info *info);
+/* Recording.calculateFileName + Long.asStringWithUnit (RecordingDao.kt:87-90, HelperComposables.kt:168-179);
+ * `timestamp` is the already formatted "yyyyMMdd-HHmmss" string. */
+int rfa_recording_file_name(const char *timestamp, const char *name, int file_format, long long frequency,
+                            long long sample_rate, char *out, int capacity);
+/* RFA_FILE_* -> RFA_FMT_* (IQ_FILE_FORMAT.md:26-84), -1 if unknown */
+int rfa_recording_sample_format(int file_format);
+
+/* FileIQSource (source/FileIQSource.java:64-91,305-369): getPacket() hands out whole packets only, rewinds when
+ * `repeat` is set, and -- with pace_sample_rate > 0 -- sleeps so that packets arrive at the hardware's rate. */
+typedef struct rfa_file_source rfa_file_source;
+int rfa_file_source_open(const char *path, int file_format, long long packet_bytes, int repeat,
+                         long long pace_sample_rate, rfa_file_source **out);
+/* 1: a packet was written to `packet`; 0: end of file; < 0: error */
+int rfa_file_source_get_packet(rfa_file_source *source, void *packet);
+long long rfa_file_source_bytes_read(const rfa_file_source *source);
+int rfa_file_source_close(rfa_file_source *source);
+
+/* Spectrum pass over frames [first_frame, first_frame + nframes) of a recording (nframes < 0: to its end) with
+ * a reader thread and two pinned buffers feeding rfa_spectrum_process: the disk read of chunk i+1 overlaps the
+ * H2D copy / kernel / D2H copy of chunk i.  out->rows (host, all rows, or NULL), out->peaks, out->avg as in
+ * rfa_spectrum_process with host buffers; chunk_frames <= 0 picks 32 MiB of IQ per chunk. */
+int rfa_spectrum_process_file(rfa_spectrum_plan *plan, const char *path, long long first_frame, long long nframes,
+                              const rfa_spectrum_out *out, long long chunk_frames, long long *frames_done);
 
 /* ---- synthetic IQ (benchmark / test input; the reference ships no input fixtures) ------ */
 /* All-integer generator of SURVEY.md 8(d): sample n depends on n alone, so any segment of a

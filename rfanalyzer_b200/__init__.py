@@ -15,7 +15,7 @@ from .engine import Context, SpectrumPlan, synth_iq, synth_step, default_synth_c
 from . import dsp
 from .dsp import (SamplePacket, Signed8BitIQConverter, Unsigned8BitIQConverter, Signed16BitIQConverter, NativeDsp,
                   FftProcessor, FftProcessorData, FirFilter, ComplexFirFilter, RationalResampler, Demodulator, AudioSink,
-                  ChainPlan)
+                  ChainPlan, FileIQSource, parse_recording_name, recording_file_name)
 
 __all__ = ["Context", "SpectrumPlan", "RfaError", "FMT_S8", "FMT_U8", "FMT_S16LE", "WIN_BLACKMAN_REF",
            "WIN_HANN", "WIN_RECT", "MEM_HOST", "MEM_DEVICE", "BYTES_PER_SAMPLE"]

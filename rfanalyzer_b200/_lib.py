@@ -37,6 +37,11 @@ class SpectrumOut(C.Structure):
                 ("peaks", C.c_void_p), ("peaks_accumulate", C.c_int), ("avg", C.c_void_p)]
 
 
+class RecordingInfo(C.Structure):
+    _fields_ = [("file_format", C.c_int), ("frequency", C.c_longlong), ("sample_rate", C.c_longlong),
+                ("have_format", C.c_int), ("have_frequency", C.c_int), ("have_sample_rate", C.c_int)]
+
+
 class RenderDesc(C.Structure):
     _fields_ = [("fft_size", C.c_int), ("frequency", C.c_longlong), ("sample_rate", C.c_int),
                 ("viewport_frequency", C.c_longlong), ("viewport_sample_rate", C.c_longlong),
@@ -105,6 +110,15 @@ SIGNATURES = {
     "rfa_demod_am": (_i, [_vp, _vp, _vp, _ll, _vp, _f, _vp, _i, _i]),
     "rfa_agc": (_i, [_vp, _vp, _ll, _vp, _f, _i, _i]),
     "rfa_mode_info": (_i, [_i, _pi, _pi, _pi, _pi]),
+    "rfa_spectrum_plan_info": (_i, [_vp, _pi, _pi, _pi]),
+    "rfa_recording_parse_name": (_i, [C.c_char_p, C.POINTER(RecordingInfo)]),
+    "rfa_recording_file_name": (_i, [C.c_char_p, C.c_char_p, _i, _ll, _ll, C.c_char_p, _i]),
+    "rfa_recording_sample_format": (_i, [_i]),
+    "rfa_file_source_open": (_i, [C.c_char_p, _i, _ll, _i, _ll, _pvp]),
+    "rfa_file_source_get_packet": (_i, [_vp, _vp]),
+    "rfa_file_source_bytes_read": (_ll, [_vp]),
+    "rfa_file_source_close": (_i, [_vp]),
+    "rfa_spectrum_process_file": (_i, [_vp, C.c_char_p, _ll, _ll, C.POINTER(SpectrumOut), _ll, _pll]),
     "rfa_render_waterfall": (_i, [_vp, C.POINTER(RenderDesc), _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "rfa_chain_create": (_i, [_vp, C.POINTER(ChainDesc), _pvp]),
     "rfa_chain_destroy": (_i, [_vp]),

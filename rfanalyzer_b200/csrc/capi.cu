@@ -440,6 +440,14 @@ int rfa_spectrum_plan_create(rfa_ctx *c, const rfa_spectrum_desc *d, rfa_spectru
     return RFA_OK;
 }
 
+int rfa_spectrum_plan_info(const rfa_spectrum_plan *pl, int *fft_size, int *format, int *avg_len) {
+    RFA_REQUIRE(pl != nullptr, "rfa_spectrum_plan_info: NULL");
+    if (fft_size) *fft_size = pl->d.fft_size;
+    if (format) *format = pl->d.format;
+    if (avg_len) *avg_len = pl->d.avg_len;
+    return RFA_OK;
+}
+
 int rfa_spectrum_plan_destroy(rfa_spectrum_plan *pl) {
     if (!pl) return RFA_OK;
     cudaSetDevice(pl->ctx->device);

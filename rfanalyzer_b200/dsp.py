@@ -590,3 +590,63 @@ class ChainPlan:
         check(self.ctx.lib.rfa_chain_process(self.handle, ptr(iq), int(nsamples), ptr(audio), int(cap), C.byref(n),
                                              _mem_of(iq, audio)))
         return n.value
+
+
+# ---- recordings on disk ---------------------------------------------------------------
+FILE_HACKRF, FILE_RTLSDR, FILE_AIRSPY, FILE_HYDRASDR = range(4)   # FilesourceFileFormat
+
+
+def parse_recording_name(ctx_or_lib, filename, file_format=FILE_HACKRF, frequency=0, sample_rate=0):
+    """MainViewModel.setFilesourceUri (MainViewModel.kt:2034-2080): (file_format, frequency, sample_rate) with
+    whatever the name carries replacing the values passed in."""
+    lib = getattr(ctx_or_lib, "lib", ctx_or_lib)
+    info = _lib.RecordingInfo(int(file_format), int(frequency), int(sample_rate), 0, 0, 0)
+    check(lib.rfa_recording_parse_name(filename.encode(), C.byref(info)))
+    return info.file_format, info.frequency, info.sample_rate
+
+
+def recording_file_name(ctx_or_lib, timestamp, name, file_format, frequency, sample_rate):
+    """Recording.calculateFileName (RecordingDao.kt:87-90)."""
+    lib = getattr(ctx_or_lib, "lib", ctx_or_lib)
+    buf = C.create_string_buffer(1024)
+    check(lib.rfa_recording_file_name(timestamp.encode(), name.encode(), int(file_format), int(frequency),
+                                      int(sample_rate), buf, len(buf)))
+    return buf.value.decode()
+
+
+class FileIQSource:
+    """FileIQSource.java:41-395 (the parts a headless run needs): init / getPacket / getBytesPerSample."""
+    FILE_FORMAT_8BIT_SIGNED, FILE_FORMAT_8BIT_UNSIGNED, FILE_FORMAT_16BIT_SIGNED = 0, 1, 2
+
+    def __init__(self, ctx_or_lib, path, sampleRate, frequency, packetSize, repeat, fileFormat, pace=False):
+        self.lib = getattr(ctx_or_lib, "lib", ctx_or_lib)
+        self.sampleRate, self.frequency, self.packetSize, self.fileFormat = sampleRate, frequency, packetSize, fileFormat
+        file_format = {0: FILE_HACKRF, 1: FILE_RTLSDR, 2: FILE_AIRSPY}[fileFormat]
+        self.handle = C.c_void_p()
+        check(self.lib.rfa_file_source_open(path.encode(), file_format, int(packetSize), 1 if repeat else 0,
+                                            int(sampleRate) if pace else 0, C.byref(self.handle)))
+        self.buffer = np.empty(packetSize, np.uint8)
+
+    def getBytesPerSample(self):
+        return 4 if self.fileFormat == self.FILE_FORMAT_16BIT_SIGNED else 2
+
+    def getPacketSize(self):
+        return self.packetSize
+
+    def getPacket(self, timeout=0):
+        """The packet buffer (reused between calls, like the reference's) or None at the end of the file."""
+        rc = self.lib.rfa_file_source_get_packet(self.handle, self.buffer.ctypes.data)
+        if rc < 0:
+            check(-rc)
+        return self.buffer if rc == 1 else None
+
+    def close(self):
+        if self.handle:
+            self.lib.rfa_file_source_close(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -192,3 +192,13 @@ class SpectrumPlan:
                                ptr(peaks), 1 if peaks_accumulate else 0, ptr(avg))
         check(self.ctx.lib.rfa_spectrum_process(self.handle, ptr(iq), int(nframes), C.byref(out),
                                                 _mem_of(iq, rows, peaks, avg)))
+
+    def process_file(self, path, first_frame=0, nframes=-1, rows=None, peaks=None, avg=None, peaks_accumulate=False,
+                     chunk_frames=0):
+        """Spectrum pass over a recording on disk (rfa_spectrum_process_file): host arrays for rows (all rows
+        of the range, or None), peaks and avg.  Returns the number of frames transformed."""
+        out = _lib.SpectrumOut(ptr(rows), 0, 1, 0, self.fft_size, 0, ptr(peaks), 1 if peaks_accumulate else 0, ptr(avg))
+        done = C.c_longlong()
+        check(self.ctx.lib.rfa_spectrum_process_file(self.handle, path.encode(), int(first_frame), int(nframes),
+                                                     C.byref(out), int(chunk_frames), C.byref(done)))
+        return done.value

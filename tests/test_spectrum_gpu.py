@@ -313,3 +313,32 @@ def test_two_pass_64x64_kernel_vs_oracle(gpu_ctx, oracle, monkeypatch, fmt):
     assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL
     assert lin_ok(rows, r)
     assert np.array_equal(peaks, rows.max(axis=0))
+
+
+@pytest.mark.parametrize("fmt,n,frames,first,count,chunk", [(0, 4096, 300, 0, -1, 64), (1, 1024, 1000, 17, 900, 0),
+                                                            (2, 2048, 123, 3, -1, 50), (0, 4096, 5, 0, -1, 2)])
+def test_process_file_matches_the_in_memory_pass(gpu_ctx, oracle, tmp_path, fmt, n, frames, first, count, chunk):
+    """rfa_spectrum_process_file: reader thread + pinned double buffers; a trailing
+    partial frame in the file is ignored; rows / peaks / avg are those of the in-memory call."""
+    import rfanalyzer_b200 as rfa
+    L = 3
+    iq = oracle.synth_iq(fmt, n * frames + 7)                    # 7 samples of a partial frame at the end
+    path = os.path.join(tmp_path, "20250111-143022_t_%s_100MHz_6MSps.iq" % ["HACKRF", "RTLSDR", "AIRSPY"][fmt])
+    iq.tofile(path)
+    total = frames - first if count < 0 else count
+    bps = rfa.BYTES_PER_SAMPLE[fmt]
+    plan = rfa.SpectrumPlan(gpu_ctx, fmt, n, avg_len=L)
+    want_rows = np.zeros((total, n), np.float32)
+    want_peaks, want_avg = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    seg = iq[first * n * bps:(first + total) * n * bps]
+    plan.process(seg, total, rows=want_rows, peaks=want_peaks, avg=want_avg)
+    rows = np.zeros((total, n), np.float32)
+    peaks, avg = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    assert plan.process_file(path, first, count, rows=rows, peaks=peaks, avg=avg, chunk_frames=chunk) == total
+    assert np.array_equal(rows, want_rows) and np.array_equal(peaks, want_peaks) and np.array_equal(avg, want_avg)
+    assert parse_name(gpu_ctx, path)[0] == [0, 1, 2][fmt]
+
+
+def parse_name(ctx, path):
+    import rfanalyzer_b200 as rfa
+    return rfa.parse_recording_name(ctx, os.path.basename(path))
