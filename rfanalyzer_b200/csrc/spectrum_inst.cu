@@ -9,11 +9,12 @@
 namespace rfa {
 namespace {
 
-template <int NL, int S, int IN, int OUT>
+template <int NL, int S, int IN, int OUT, bool STAGED = false>
 cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *spc_out) {
     using G = Geom<NL>;
-    constexpr size_t SMEM = SpectrumFrame<NL, S, IN, OUT>::SMEM_BYTES;
-    auto kern = spectrum_kernel<NL, S, IN, OUT>;
+    constexpr size_t SMEM = STAGED ? staged_offset<NL, S, IN, OUT>() + staged_bytes<NL, IN>()
+                                   : SpectrumFrame<NL, S, IN, OUT>::SMEM_BYTES;
+    auto kern = spectrum_kernel<NL, S, IN, OUT, STAGED>;
     static bool configured = false;
     cudaError_t err;
     if (!configured) {
@@ -48,6 +49,13 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     if (avg_cta) grid += 1;
     kern<<<(unsigned)grid, G::CTA, SMEM, L.stream>>>(L.p);
     return cudaGetLastError();
+}
+
+// TMA-staged input (spectrum_kernel.cuh, STAGED): N = 1024 .. 4096, integer formats, 16-byte aligned IQ.
+// RFA_STAGED=0 switches it off (A/B timing runs).
+static bool staged_enabled(const void *iq) {
+    const char *e = getenv("RFA_STAGED");
+    return !(e && atoi(e) == 0) && ((size_t)iq & 15) == 0;
 }
 
 // dual-frame kernel (spectrum2_kernel.cuh): one 256-thread CTA per SM, two frames per thread
@@ -136,6 +144,15 @@ cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc
     if (L.out_kind == OUT_CPLX) {
         if (L.in_fmt == FMT_CF32) return launch_one<NL, S, FMT_CF32, OUT_CPLX>(L, query, grid, spc);
         return cudaErrorInvalidValue;
+    }
+    if constexpr (S == 1 && NL >= 1024 && NL <= 4096) {
+        if (staged_enabled(L.p.in)) {
+            switch (L.in_fmt) {
+                case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB, true>(L, query, grid, spc);
+                case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB, true>(L, query, grid, spc);
+                case FMT_S16LE: return launch_one<NL, S, FMT_S16LE, OUT_DB, true>(L, query, grid, spc);
+            }
+        }
     }
     switch (L.in_fmt) {
         case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB>(L, query, grid, spc);

@@ -324,6 +324,39 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
         atomicMin((unsigned int *)addr, __float_as_uint(v));
 }
 
+// ---- TMA-staged raw IQ (STAGED kernels): the raw codes of a chunk arrive in shared memory by one bulk
+// copy (UBLKCP, completion on an mbarrier) issued by a single thread two iterations ahead, instead of
+// 16 two-byte LDGs per thread held in 16 registers for a whole iteration.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *mbar) {
+    // the buffer was last read through the generic proxy (LDS) before the barrier this thread just passed
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(mbar)), "r"(parity)
+                     : "memory");
+}
+// the bulk copy thread 0 issues right after the first exchange barrier of an iteration (everybody has
+// consumed the buffer it refills by then)
+struct StageNext {
+    void *dst = nullptr;
+    const void *src = nullptr;
+    uint32_t bytes = 0;
+    unsigned long long *mbar = nullptr;
+};
+
 // Passes 1 .. PASSES-1 of one frame.  With two shared frames (NBUF == 2) pass k scatters into
 // buffer (k-1)&1 and gathers from it after ONE barrier: the buffer being overwritten was last
 // read two barriers ago.  With a single frame a second barrier protects the gather.
@@ -332,7 +365,7 @@ struct MiddlePasses {
     // tw_mid: tables of the middle passes (shared-memory copy when it fits), tw_all: the
     // complete global table (the last pass reads it when its twiddles are not in registers)
     static __device__ __forceinline__ void run(cf *x0, cf *x1, const cf *tw_mid, const cf *tw_all, const cf *twreg,
-                                               int tid, cf *u, int tbase = 0) {
+                                               int tid, cf *u, int tbase = 0, const StageNext *sn = nullptr) {
         using F = SpectrumFrame<NL, S, IN, OUT>;
         if constexpr (PASS < Plan<NL>::PASSES) {
             cf *x = ((PASS - 1) & 1) ? x1 : x0;
@@ -341,6 +374,7 @@ struct MiddlePasses {
             RFA_STAMP(tbase + 2 * PASS - 1);  // scatter issued
             __syncthreads();
             RFA_STAMP(tbase + 2 * PASS);      // barrier passed
+            if (PASS == 1 && sn != nullptr && sn->bytes != 0 && threadIdx.x == 0) tma_load_1d(sn->dst, sn->src, sn->bytes, sn->mbar);
 #endif
             if constexpr (PASS == F::LAST && F::LAST_TW_REG)
                 F::gather_last_reg(x, twreg, tid, u);
@@ -428,13 +462,35 @@ __device__ __forceinline__ void retire_cta(const SpectrumParams &p) {
     }
 }
 
+// bytes of shared memory a STAGED kernel needs on top of SpectrumFrame::SMEM_BYTES: two chunk buffers
+template <int NL, int IN>
+RFA_CX size_t staged_bytes() {
+    return 2 * (size_t)Geom<NL>::FPC * NL * in_elem_bytes<IN>();
+}
 template <int NL, int S, int IN, int OUT>
+RFA_CX size_t staged_offset() {  // 128-byte aligned start of the chunk buffers
+    return (SpectrumFrame<NL, S, IN, OUT>::SMEM_BYTES + 127) / 128 * 128;
+}
+
+// chunk q of a STAGED kernel: the block of valid frames it covers, as (first frame, bytes)
+template <int NL, int FPC, int BPS>
+__device__ __forceinline__ void chunk_block(long long nframes, int q, long long *f_start, uint32_t *bytes) {
+    const long long f_hi = nframes - 1 - (long long)q * FPC;  // newest frame of the chunk (sub = 0)
+    long long f_lo = f_hi - (FPC - 1);
+    if (f_lo < 0) f_lo = 0;
+    *f_start = f_lo;
+    *bytes = f_hi >= f_lo ? (uint32_t)((f_hi - f_lo + 1) * (long long)NL * BPS) : 0u;
+}
+
+template <int NL, int S, int IN, int OUT, bool STAGED = false>
 __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINCTAS : 1) spectrum_kernel(const SpectrumParams p) {
     using G = Geom<NL>;
     using F = SpectrumFrame<NL, S, IN, OUT>;
     constexpr int T = G::T, E = G::E, FPC = G::FPC, N = NL * S;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(!STAGED || (F::PREFETCH && S == 1), "staging is for the integer formats");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_chunk[2];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
     RFA_STAMP(0);
     const bool want_avg = (OUT == OUT_DB) && p.avg != nullptr;
     const bool want_peak = (OUT == OUT_DB) && p.peaks != nullptr;
@@ -458,7 +514,23 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     int q = group, q_next = group + groups, q_next2 = group + 2 * groups;
     cf u[E];
     uint32_t raw[F::PREFETCH ? E : 1];
-    if constexpr (F::PREFETCH) {  // first: get the raw IQ of the first frame moving
+    constexpr size_t CHUNK_BYTES = (size_t)FPC * NL * BPS;
+    unsigned char *stage = smem_raw + staged_offset<NL, S, IN, OUT>();  // [2][CHUNK_BYTES] (STAGED)
+    if constexpr (STAGED) {  // the first two chunks start moving before anything else
+        if (threadIdx.x == 0) {
+            mbar_init(&s_mbar[0]);
+            mbar_init(&s_mbar[1]);
+            const int qs[2] = {q, q_next};
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                long long f0;
+                uint32_t bytes;
+                chunk_block<NL, FPC, BPS>(p.nframes, qs[b], &f0, &bytes);
+                if (qs[b] < nchunks && bytes)
+                    tma_load_1d(stage + b * CHUNK_BYTES, (const char *)p.in + f0 * (long long)NL * BPS, bytes, &s_mbar[b]);
+            }
+        }
+    } else if constexpr (F::PREFETCH) {  // first: get the raw IQ of the first frame moving
         const long long v = (long long)q * FPC + sub;
         if (v < p.nframes) F::load_raw((const char *)p.in + ((p.nframes - 1 - v) * (long long)N + tid) * BPS, raw);
     }
@@ -505,7 +577,25 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
             s_chunk[it & 1] = 3 * groups + (int)pending;
             pending = atomicAdd(p.ticket + TICKET_WORK + c, 1u);
         }
-        if constexpr (F::PREFETCH) {
+        StageNext sn;
+        if constexpr (STAGED) {
+            // this chunk's raw IQ sits in buffer it & 1 (copy issued two iterations ago); the buffer is
+            // refilled with chunk q_next2 right after the first exchange barrier of this iteration
+            long long f0;
+            uint32_t bytes;
+            chunk_block<NL, FPC, BPS>(p.nframes, q, &f0, &bytes);
+            mbar_wait(&s_mbar[it & 1], (uint32_t)((it >> 1) & 1));
+            if (active) {
+                F::load_raw((const char *)(stage + (it & 1) * CHUNK_BYTES) + ((f - f0) * (long long)NL + tid) * BPS, raw);
+                F::first_from_raw(raw, wreg, u);
+            }
+            if (q_next2 < nchunks) {
+                chunk_block<NL, FPC, BPS>(p.nframes, q_next2, &f0, &sn.bytes);
+                sn.dst = stage + (it & 1) * CHUNK_BYTES;
+                sn.src = (const char *)p.in + f0 * (long long)NL * BPS;
+                sn.mbar = &s_mbar[it & 1];
+            }
+        } else if constexpr (F::PREFETCH) {
             if (active) F::first_from_raw(raw, wreg, u);
             const long long vn = (long long)q_next * FPC + sub;  // lands while this frame is transformed
             if (vn < p.nframes) F::load_raw((const char *)p.in + ((p.nframes - 1 - vn) * (long long)N + tid) * BPS, raw);
@@ -517,7 +607,7 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
         // the passes already order it (PASSES-1 exchanges alternate A,B,A,...)
         if (it > 0 && (G::NBUF == 1 || ((Plan<NL>::PASSES - 1) & 1))) __syncthreads();
         if constexpr (Plan<NL>::PASSES > 1)
-            MiddlePasses<NL, S, IN, OUT, 1>::run(x0, x1, tw, p.tw, twreg, tid, u, 8 + 8 * it);
+            MiddlePasses<NL, S, IN, OUT, 1>::run(x0, x1, tw, p.tw, twreg, tid, u, 8 + 8 * it, STAGED ? &sn : nullptr);
         else
             __syncthreads();
         RFA_STAMP(8 + 8 * it + 6);
