@@ -291,18 +291,65 @@ struct Dft<16> {
     static RFA_CX int perm(int c) { return 4 * (c & 3) + (c >> 2); }
 };
 
+template <>
+struct Dft<32> {
+    // 2 x 16: DFT16 over the even and the odd inputs, twiddle W32^k1 on the odd half, radix-2 combine.
+    // Natural order in, natural order out (everything is registers: the copies are renamings).
+    template <class V>
+    static RFA_HD void run(V *u) {
+        V e[16], o[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            e[i] = u[2 * i];
+            o[i] = u[2 * i + 1];
+        }
+        Dft<16>::run(e);
+        Dft<16>::run(o);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int p = Dft<16>::perm(k);
+            V t = o[p];
+            if (k == 8)
+                t = mul_mj(t);
+            else if (k > 0)
+                t = cmul(t, w32(k));
+            u[k] = cadd(e[p], t);
+            u[k + 16] = csub(e[p], t);
+        }
+    }
+    static RFA_CX int perm(int c) { return c; }
+    static RFA_HD cf w32(int k) {  // exp(-2*pi*i*k/32), 0 < k < 16
+        const float c[9] = {1.0f,
+                            0.98078528040323044913f,
+                            0.92387953251128675613f,
+                            0.83146961230254523708f,
+                            0.70710678118654752440f,
+                            0.55557023301960222474f,
+                            0.38268343236508977173f,
+                            0.19509032201612826785f,
+                            0.0f};
+        return k <= 8 ? cf{c[k], -c[8 - k]} : cf{-c[16 - k], -c[k - 8]};
+    }
+};
+
 // ---------------------------------------------------------------------------
 // Frame geometry.  NL = points transformed inside one CTA slot (shared memory),
 // T = threads cooperating on the frame, E = NL/T points per thread.
 // Radix plan: as many radix-16 passes as fit, then one radix-2/4/8 pass.
 // ---------------------------------------------------------------------------
+// Radix plan of an n-point transform, shared by the kernels (Plan<NL>) and the host table builder
+// (make_pass_twiddles): as many radix-16 passes as fit, then one radix-2/4/8 pass -- except for
+// 16384 points, where a thread holds 32 points and 16 x 32 x 32 saves a whole pass (and exchange).
+RFA_CX int plan_passes(int lg) { return lg == 14 ? 3 : lg / 4 + (lg % 4 ? 1 : 0); }
+RFA_CX int plan_radix(int lg, int pass) {
+    return lg == 14 ? (pass == 0 ? 16 : 32) : (pass < lg / 4 ? 16 : (1 << (lg % 4)));
+}
+
 template <int NL>
 struct Plan {
     static constexpr int LG = ilog2c(NL);
-    static constexpr int N16 = LG / 4;
-    static constexpr int REM = LG % 4;
-    static constexpr int PASSES = N16 + (REM ? 1 : 0);
-    static RFA_CX int radix(int pass) { return pass < N16 ? 16 : (1 << REM); }
+    static constexpr int PASSES = plan_passes(LG);
+    static RFA_CX int radix(int pass) { return plan_radix(LG, pass); }
     // product of the radices of all passes before `pass`
     static RFA_CX int prod(int pass) { return pass == 0 ? 1 : prod(pass - 1) * radix(pass - 1); }
     // padded shared-memory frame: one pad slot per 16 points keeps the radix-R

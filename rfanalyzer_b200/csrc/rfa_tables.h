@@ -40,11 +40,11 @@ inline std::vector<cf> make_pass_twiddles(int NL) {
     const double PI = 3.14159265358979323846;
     int lg = 0;
     while ((1 << lg) < NL) lg++;
-    const int n16 = lg / 4, rem = lg % 4, passes = n16 + (rem ? 1 : 0);
+    const int passes = plan_passes(lg);
     std::vector<cf> out;
     int P = 1;
     for (int pass = 0; pass < passes; pass++) {
-        const int R = pass < n16 ? 16 : (1 << rem);
+        const int R = plan_radix(lg, pass);
         if (pass >= 1)
             for (int r = 1; r < R; r++)
                 for (int k = 0; k < P; k++) {
