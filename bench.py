@@ -209,6 +209,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: whatever NCCL logs (NCCL_DEBUG=VERSION/INFO on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     window = rfa.WIN_HANN if args.window == "hann" else rfa.WIN_BLACKMAN_REF
