@@ -177,6 +177,22 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(index):
+    """Run this rank's host side (and first-touch its pinned buffers) on the CPUs next to its GPU: with eight ranks
+    streaming 96 MiB per step each over PCIe, buffers on the far socket halve the end-to-end rate."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass  # no NVML or no affinity information: keep the inherited CPU set
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -207,6 +223,7 @@ def main():
         raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "
                          "--master-addr 127.0.0.1 --master-port P bench.py --gpus %d ..." % (args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: whatever NCCL logs (NCCL_DEBUG=VERSION/INFO on some boxes) goes to stderr

@@ -29,6 +29,7 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     if (err != cudaSuccess) return err;
     if (occ < 1) occ = 1;
     long long need = ((L.p.nframes + G::FPC - 1) / G::FPC) * S;
+    if (need / S > 0x7FFF0000LL) return cudaErrorInvalidValue;  // chunk indices are 32-bit in the kernel
     long long cap = (long long)L.num_sms * occ;
     static const int maxgrid_env = [] {  // tuning runs only
         const char *e = getenv("RFA_MAXGRID");
@@ -77,6 +78,7 @@ cudaError_t launch_two(const SpectrumLaunch &L, bool query, int *grid_out, int *
     if (occ < 1) occ = 1;
     const long long npairs = (L.p.nframes + 1) / 2;
     long long need = (npairs + G::FPC - 1) / G::FPC;
+    if (need > 0x7FFF0000LL) return cudaErrorInvalidValue;  // chunk indices are 32-bit in the kernel
     long long cap = (long long)L.num_sms * occ;
     if (L.max_grid > 0 && L.max_grid < cap) cap = L.max_grid;
     const bool avg_cta = L.p.avg != nullptr;  // the averaging CTA takes one resident slot
