@@ -357,6 +357,7 @@ struct rfa_spectrum_plan {
     const cf *tw = nullptr, *twN = nullptr;
     const float *win = nullptr;
     Buf ticket;     // finished-tail-row counters of the fused kernel
+    Buf zbuf;       // four-step intermediate (N >= 32768)
     Buf tail;       // (L+1) rows when the caller stores no rows
     Buf dpeaks;     // device running peaks (host mode)
     Buf davg;       // device average (host mode)
@@ -406,6 +407,33 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
         RFA_CK(cudaGetLastError());
         c->launches++;
     }
+    if (fourstep_supported(n, pl->d.format, OUT_DB)) {
+        // N = 32768 / 65536: column transforms, twiddle, row transforms through an intermediate buffer
+        // (fourstep_kernel.cuh); the time average is a row reduction afterwards.  Measured on B200 the fixed cost
+        // of a launch pair (persistent-CTA prologue and tail) outweighs keeping the intermediate inside L2:
+        // 2^24 samples take 92 / 99 us as one 128 MiB batch, 109 / 119 us as four 32 MiB batches.
+        FourStepLaunch fs{};
+        if (int rc = c->get_twiddles(n / 256, &fs.tw_n1)) return rc;
+        if (int rc = c->get_twiddles(256, &fs.tw_256)) return rc;
+        fs.tw_n = pl->twN;
+        const char *eb = getenv("RFA_FS_BATCH_KIB");  // tuning runs and the multi-batch test; read per call
+        long long want = (long long)(eb && atoi(eb) > 0 ? atoi(eb) : 128 << 10) << 10;  // default: 128 MiB per batch
+        const long long all = nframes * (long long)n * (long long)sizeof(cf);
+        if (want > all) want = all;
+        if (want < (long long)n * (long long)sizeof(cf)) want = (long long)n * (long long)sizeof(cf);
+        if (int rc = pl->zbuf.ensure((size_t)want)) return rc;
+        fs.z = pl->zbuf.as<cf>();
+        fs.z_bytes = want;
+        cudaError_t e4 = fourstep_launch(L, fs);
+        if (e4 != cudaSuccess) return cuda_fail(e4, "four-step spectrum kernels");
+        c->launches += fourstep_launches(n, nframes, fs.z_bytes);
+        if (aq.avg) {
+            average_rows(rows, L.p.avg_newest, L.p.avg_dir, ring_rows, row_stride, aq.valid, pl->d.avg_len, n, aq.avg, c->stream);
+            RFA_CK(cudaGetLastError());
+            c->launches++;
+        }
+        return RFA_OK;
+    }
     cudaError_t e = spectrum_launch(L);
     if (e != cudaSuccess) return cuda_fail(e, "spectrum kernel");
     c->launches++;
@@ -454,6 +482,7 @@ int rfa_spectrum_plan_destroy(rfa_spectrum_plan *pl) {
     cudaStreamSynchronize(pl->ctx->stream);
     pl->tail.release();
     pl->ticket.release();
+    pl->zbuf.release();
     pl->dpeaks.release();
     pl->davg.release();
     for (int i = 0; i < 2; i++) {

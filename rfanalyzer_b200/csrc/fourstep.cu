@@ -1,0 +1,107 @@
+// fourstep.cu -- launcher of the four-step spectrum path (fourstep_kernel.cuh) for N = 32768, 65536.
+#include <stdlib.h>
+
+#include "fourstep_kernel.cuh"
+#include "spectrum_launch.h"
+
+namespace rfa {
+namespace {
+
+// K is a function-pointer TYPE (the same for every kernel of this file), so nothing here may be static
+template <class K>
+cudaError_t resident_ctas(K kern, size_t smem, int *occ) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, 256, smem);
+    if (e == cudaSuccess && *occ < 1) *occ = 1;
+    return e;
+}
+
+template <int N1, int IN>
+cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
+    using G = GeomFS<N1>;
+    auto ka = fourstep_cols_kernel<N1, IN>;
+    auto kb = fourstep_rows_kernel<N1>;
+    static thread_local int dev_done = -1, occ_a = 1, occ_b = 1;  // per instantiation <N1, IN>, per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev_done != dev) {
+        e = resident_ctas(ka, G::SMEM_A, &occ_a);
+        if (e != cudaSuccess) return e;
+        e = resident_ctas(kb, G::SMEM_B, &occ_b);
+        if (e != cudaSuccess) return e;
+        dev_done = dev;
+    }
+    const long long batch = fs.z_bytes / ((long long)G::N * (long long)sizeof(cf));
+    if (batch < 1) return cudaErrorInvalidValue;
+    const char *ep = getenv("RFA_FS_PDL");  // RFA_FS_PDL=0: plain stream order (A/B timing runs)
+    const bool pdl = !(ep && atoi(ep) == 0);
+    FourStepParams a{};
+    a.p = L.p;
+    a.tw_n1 = fs.tw_n1;
+    a.tw_256 = fs.tw_256;
+    a.tw_n = fs.tw_n;
+    a.z = fs.z;
+    for (long long f0 = 0; f0 < L.p.nframes; f0 += batch) {
+        const long long nb = L.p.nframes - f0 < batch ? L.p.nframes - f0 : batch;
+        a.frame0 = f0;
+        a.nbatch = (int)nb;
+        long long lanes_a = (long long)L.num_sms * occ_a / G::GROUPS_A, lanes_b = (long long)L.num_sms * occ_b / G::GROUPS_B;
+        if (lanes_a < 1) lanes_a = 1;
+        if (lanes_b < 1) lanes_b = 1;
+        if (lanes_a > nb) lanes_a = nb;
+        if (lanes_b > nb) lanes_b = nb;
+        // both launches carry the programmatic-serialization attribute: their prologues overlap the drain of
+        // the kernel before them, griddepcontrol.wait in the kernels orders every access to shared data
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(256);
+        cfg.stream = L.stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)(lanes_a * G::GROUPS_A));
+        cfg.dynamicSmemBytes = G::SMEM_A;
+        e = cudaLaunchKernelEx(&cfg, ka, a);
+        if (e != cudaSuccess) return e;
+        cfg.gridDim = dim3((unsigned)(lanes_b * G::GROUPS_B));
+        cfg.dynamicSmemBytes = G::SMEM_B;
+        e = cudaLaunchKernelEx(&cfg, kb, a);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+template <int N1>
+cudaError_t run_fmt(const SpectrumLaunch &L, const FourStepLaunch &fs) {
+    switch (L.in_fmt) {
+        case FMT_S8: return run<N1, FMT_S8>(L, fs);
+        case FMT_U8: return run<N1, FMT_U8>(L, fs);
+        case FMT_S16LE: return run<N1, FMT_S16LE>(L, fs);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool fourstep_supported(int N, int in_fmt, int out_kind) {
+    const char *e = getenv("RFA_FOURSTEP");  // RFA_FOURSTEP=0: the residue-split kernel (A/B timing runs)
+    if (e && atoi(e) == 0) return false;
+    return (N == 32768 || N == 65536) && out_kind == OUT_DB && (in_fmt == FMT_S8 || in_fmt == FMT_U8 || in_fmt == FMT_S16LE);
+}
+
+int fourstep_launches(int N, long long nframes, long long z_bytes) {
+    const long long batch = z_bytes / ((long long)N * (long long)sizeof(cf));
+    return batch < 1 ? 0 : (int)(2 * ((nframes + batch - 1) / batch));
+}
+
+cudaError_t fourstep_launch(const SpectrumLaunch &L, const FourStepLaunch &fs) {
+    if (L.p.nframes <= 0) return cudaSuccess;
+    return L.N == 65536 ? run_fmt<256>(L, fs) : run_fmt<128>(L, fs);
+}
+
+}  // namespace rfa

@@ -1,0 +1,239 @@
+// fourstep_kernel.cuh -- the fused IQ -> spectrum path for N = 32768 and 65536 as a four-step FFT.
+//
+// Same reference lines as spectrum_kernel.cuh; what changes is the factorisation.  A frame of
+// N = N1 * 256 points does not fit one SM's shared memory, and the residue split of spectrum_kernel
+// re-reads, re-converts and re-windows the input S times.  Here, with n = 256*n1 + n2 and
+// k = k1 + N1*k2:
+//
+//   step A (columns)  Y[k1][n2] = sum_n1 w[n] x[n] W_N1^(n1 k1)      256 FFTs of N1 points, stride 256
+//                     Z[k1][n2] = Y[k1][n2] * W_N^(n2 k1)            twiddle, written row-major
+//   step B (rows)     X[k1 + N1 k2] = sum_n2 Z[k1][n2] W_256^(n2 k2) N1 FFTs of 256 points
+//                     dB, fft-shift, row store, peak hold
+//
+// Z (8 bytes per point) lives in a batch buffer of at most 128 MiB (2^24 points): most of it is still in
+// the 126 MB L2 when step B reads it back; the IQ bytes are read once and the rows written once, like
+// everywhere else.  The two kernels of a batch are chained by programmatic dependent launch.
+// Thread layouts put neighbouring COLUMNS (step A) resp. neighbouring ROWS (step B) on neighbouring
+// lanes, so that the strided side of each step is the coalesced one; per-column / per-row exchange
+// buffers have an odd stride, which keeps every shared-memory access conflict-free.  A CTA keeps its
+// column (row) group for the whole launch: window taps, twiddles and running peaks stay in registers.
+#pragma once
+#include "spectrum_kernel.cuh"
+
+namespace rfa {
+
+struct FourStepParams {
+    SpectrumParams p;      // in, win, rows, row0/row_step/ring_rows/row_stride, store_from, peaks, inv_n2 (dB bias)
+    const cf *tw_n1;       // per-pass Stockham twiddles of an N1-point transform (make_pass_twiddles(N1))
+    const cf *tw_256;      // ... of a 256-point transform
+    const cf *tw_n;        // exp(-2*pi*i*t/N), t < N
+    cf *z;                 // [batch][N1][256]
+    long long frame0;      // first frame of this batch
+    int nbatch;            // frames in this batch
+};
+
+template <int N1>
+struct GeomFS {
+    static constexpr int N = N1 * 256;
+    static constexpr int T1 = N1 / 16;           // threads per column transform (16 points each)
+    static constexpr int CPC = 256 / T1;         // columns per CTA (step A)
+    static constexpr int GROUPS_A = 256 / CPC;   // column groups
+    static constexpr int GROUPS_B = N1 / 16;     // row groups of 16 rows (step B)
+    static constexpr int CSTRIDE = (Plan<N1>::SMEM_POINTS | 1);   // odd: lanes = columns
+    static constexpr int RSTRIDE = (Plan<256>::SMEM_POINTS | 1);  // odd: lanes = rows
+    static constexpr int TSTRIDE = 257;                           // staged Z tile, odd
+    static constexpr size_t SMEM_A = (size_t)CPC * CSTRIDE * sizeof(cf);
+    static constexpr size_t SMEM_B = (size_t)16 * (RSTRIDE + TSTRIDE) * sizeof(cf);
+    static_assert(N1 == 128 || N1 == 256, "four-step covers N = 32768 and 65536");
+    static_assert(Plan<N1>::PASSES == 2 && Plan<256>::PASSES == 2, "two passes per step");
+};
+
+// ---- step A: one column, thread t of its T1 threads -------------------------------------------
+template <int N1, int IN>
+struct FourStepA {
+    using G = GeomFS<N1>;
+    static constexpr int T1 = G::T1, R1 = Plan<N1>::radix(1), NB = 16 / R1;
+    // raw codes of points n1 = t + r*T1 of column n2; `src` points at sample n2 + 256*t of the frame
+    static RFA_HD void load_raw(const char *src, uint32_t *raw) {
+#pragma unroll
+        for (int r = 0; r < 16; r++)
+            raw[r] = (IN == FMT_S16LE) ? ((const uint32_t *)src)[(size_t)r * T1 * 256] : (uint32_t)((const uint16_t *)src)[(size_t)r * T1 * 256];
+    }
+    static RFA_HD void load_window(const float *win, int n2, int t, float *wreg) {
+#pragma unroll
+        for (int r = 0; r < 16; r++) wreg[r] = (win ? win[(t + r * T1) * 256 + n2] : 1.0f) * unit_scale<IN>();
+    }
+    // Stockham twiddles of the second pass (frame-invariant): twreg[b*(R1-1) + r-1]
+    static RFA_HD void load_pass_tw(const cf *tw_n1, int t, cf *twreg) {
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int r = 1; r < R1; r++) twreg[b * (R1 - 1) + r - 1] = tw_n1[(r - 1) * 16 + ((t + b * T1) & 15)];
+    }
+    // output e = b*R1 + c of this thread is k1 = (t + b*T1) + 16*c
+    static RFA_HD int k1_of(int t, int e) { return (t + (e / R1) * T1) + 16 * (e % R1); }
+    static RFA_HD void load_col_tw(const cf *tw_n, int n2, int t, cf *twz) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) twz[e] = tw_n[(n2 * k1_of(t, e)) & (G::N - 1)];
+    }
+    static RFA_HD void first(const uint32_t *raw, const float *wreg, cf *u) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) u[e] = decode_point<IN>(raw[e], wreg[e]);
+        Dft<16>::run(u);
+    }
+    static RFA_HD void scatter(cf *xcol, int t, const cf *u) { pass_scatter<N1, T1, 16, 1>(xcol, t, u); }
+    // second pass + column twiddle; z points at Z[frame][0][n2]
+    static RFA_HD void second(const cf *xcol, const cf *twreg, const cf *twz, int t, cf *u, cf *z) {
+        constexpr int STR = N1 / R1;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const cf *xi = xcol + phys(t + b * T1);
+#pragma unroll
+            for (int r = 0; r < R1; r++) {
+                cf v = xi[r * (STR + STR / 16)];
+                if (r > 0) v = cmul(v, twreg[b * (R1 - 1) + r - 1]);
+                u[b * R1 + r] = v;
+            }
+            Dft<R1>::run(u + b * R1);
+#pragma unroll
+            for (int c = 0; c < R1; c++) {
+                const int e = b * R1 + c;
+                z[(size_t)k1_of(t, e) * 256] = cmul(u[b * R1 + Dft<R1>::perm(c)], twz[e]);
+            }
+        }
+    }
+};
+
+// ---- step B: one row k1, thread t of its 16 threads ----------------------------------------------
+template <int N1>
+struct FourStepB {
+    using G = GeomFS<N1>;
+    static RFA_HD void load_pass_tw(const cf *tw_256, int t, cf *twreg) {
+#pragma unroll
+        for (int r = 1; r < 16; r++) twreg[r - 1] = tw_256[(r - 1) * 16 + t];
+    }
+    // first pass from the staged row (points n2 = t + 16*r)
+    static RFA_HD void first(const cf *zrow, int t, cf *u) {
+#pragma unroll
+        for (int r = 0; r < 16; r++) u[r] = zrow[t + 16 * r];
+        Dft<16>::run(u);
+    }
+    static RFA_HD void scatter(cf *xrow, int t, const cf *u) { pass_scatter<256, 16, 16, 1>(xrow, t, u); }
+    // second pass, dB, store and peak: output c is k2 = t + 16*c, bin = (k1 + N1*k2) ^ (N/2)
+    template <bool PEAK, bool STORE>
+    static RFA_HD void second(const cf *xrow, const cf *twreg, int t, int k1, float *out, float *pk, float db_bias) {
+        cf u[16];
+        const cf *xi = xrow + phys(t);
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            cf v = xi[r * 17];
+            if (r > 0) v = cmul(v, twreg[r - 1]);
+            u[r] = v;
+        }
+        Dft<16>::run(u);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const float db = logmag_db(u[Dft<16>::perm(c)], db_bias);
+            if (STORE) out[bin_of(t, k1, c)] = db;
+            if (PEAK) pk[c] = fmaxf(pk[c], db);
+        }
+    }
+    static RFA_HD int bin_of(int t, int k1, int c) { return (k1 + N1 * (t + 16 * c)) ^ (G::N >> 1); }
+};
+
+#ifdef __CUDACC__
+#ifndef RFA_FS_MINCTAS
+#define RFA_FS_MINCTAS 2  // two resident column CTAs per SM (128 registers; 144 without the cap)
+#endif
+// PTX griddepcontrol (sm_90+): no-ops when the kernel was launched without the programmatic-serialization attribute
+__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// grid = GROUPS_A * lanes; CTA (group, lane) transforms column group `group` of frames lane, lane+lanes, ...
+template <int N1, int IN>
+__global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(const FourStepParams a) {
+    using G = GeomFS<N1>;
+    using F = FourStepA<N1, IN>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int col = threadIdx.x % G::CPC, t = threadIdx.x / G::CPC;
+    const int group = blockIdx.x % G::GROUPS_A, lane = blockIdx.x / G::GROUPS_A, lanes = gridDim.x / G::GROUPS_A;
+    const int n2 = group * G::CPC + col;
+    cf *xcol = reinterpret_cast<cf *>(smem_raw) + (size_t)col * G::CSTRIDE;
+    constexpr int BPS = in_elem_bytes<IN>();
+    float wreg[16];
+    cf twreg[F::NB * (F::R1 - 1)], twz[16], u[16];
+    uint32_t raw[16];
+    // programmatic dependent launch: the next kernel of the chain may start its (constant-table) prologue while
+    // this grid drains; everything that touches Z, the IQ bytes, rows or peaks sits behind grid_dependency_wait()
+    launch_dependents();
+    F::load_window(a.p.win, n2, t, wreg);
+    F::load_pass_tw(a.tw_n1, t, twreg);
+    F::load_col_tw(a.tw_n, n2, t, twz);
+    grid_dependency_wait();
+    const char *src0 = (const char *)a.p.in + ((size_t)t * 256 + n2) * BPS;
+    if (lane < a.nbatch) F::load_raw(src0 + (a.frame0 + lane) * (long long)G::N * BPS, raw);
+    for (int fb = lane; fb < a.nbatch; fb += lanes) {
+        F::first(raw, wreg, u);
+        if (fb + lanes < a.nbatch) F::load_raw(src0 + (a.frame0 + fb + lanes) * (long long)G::N * BPS, raw);
+        __syncthreads();  // the previous frame's second pass has read the exchange buffer
+        F::scatter(xcol, t, u);
+        __syncthreads();
+        F::second(xcol, twreg, twz, t, u, a.z + (size_t)fb * G::N + n2);
+    }
+}
+
+// grid = GROUPS_B * lanes; CTA (group, lane) transforms rows 16*group .. 16*group+15 of its frames
+template <int N1>
+__global__ void __launch_bounds__(256) fourstep_rows_kernel(const FourStepParams a) {
+    using G = GeomFS<N1>;
+    using F = FourStepB<N1>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int row = threadIdx.x % 16, t = threadIdx.x / 16;
+    const int group = blockIdx.x % G::GROUPS_B, lane = blockIdx.x / G::GROUPS_B, lanes = gridDim.x / G::GROUPS_B;
+    const int k1 = group * 16 + row;
+    cf *xs = reinterpret_cast<cf *>(smem_raw);             // [16][RSTRIDE] exchange
+    cf *tile = xs + 16 * G::RSTRIDE;                        // [16][TSTRIDE] staged rows of Z
+    cf twreg[15];
+    launch_dependents();
+    F::load_pass_tw(a.tw_256, t, twreg);
+    grid_dependency_wait();
+    float pk[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) pk[c] = -999999.0f;
+    const bool want_peak = a.p.peaks != nullptr;
+    bool worked = false;
+    for (int fb = lane; fb < a.nbatch; fb += lanes) {
+        const long long f = a.frame0 + fb;
+        // stage the 16 rows (32 KB, contiguous in Z) with coalesced loads
+        const cf *zt = a.z + (size_t)fb * G::N + (size_t)group * 16 * 256;
+        __syncthreads();  // the previous frame's passes are done with both buffers
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int idx = threadIdx.x + 256 * j;
+            tile[(idx >> 8) * G::TSTRIDE + (idx & 255)] = zt[idx];
+        }
+        __syncthreads();
+        cf u[16];
+        F::first(tile + row * G::TSTRIDE, t, u);
+        F::scatter(xs + row * G::RSTRIDE, t, u);
+        __syncthreads();
+        float *out = a.p.rows + frame_row(a.p, f) * a.p.row_stride;
+        const cf *xrow = xs + row * G::RSTRIDE;
+        if (f >= a.p.store_from) {
+            if (want_peak)
+                F::template second<true, true>(xrow, twreg, t, k1, out, pk, a.p.inv_n2);
+            else
+                F::template second<false, true>(xrow, twreg, t, k1, out, pk, a.p.inv_n2);
+        } else if (want_peak) {
+            F::template second<true, false>(xrow, twreg, t, k1, out, pk, a.p.inv_n2);
+        }
+        worked = true;
+    }
+    if (want_peak && worked) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) atomic_max_float(a.p.peaks + F::bin_of(t, k1, c), pk[c]);
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace rfa

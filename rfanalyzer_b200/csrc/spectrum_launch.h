@@ -27,6 +27,18 @@ cudaError_t spectrum_group1(const SpectrumLaunch &L, bool query, int *grid, int 
 cudaError_t spectrum_group2(const SpectrumLaunch &L, bool query, int *grid, int *spc);
 cudaError_t spectrum_group3(const SpectrumLaunch &L, bool query, int *grid, int *spc);
 
+// four-step path for N = 32768 / 65536 (fourstep.cu): rows, peaks; the caller averages afterwards
+struct FourStepLaunch {
+    const cf *tw_n1;    // make_pass_twiddles(N / 256)
+    const cf *tw_256;   // make_pass_twiddles(256)
+    const cf *tw_n;     // make_twiddles(N)
+    cf *z;              // batch buffer
+    long long z_bytes;
+};
+bool fourstep_supported(int N, int in_fmt, int out_kind);
+int fourstep_launches(int N, long long nframes, long long z_bytes);
+cudaError_t fourstep_launch(const SpectrumLaunch &L, const FourStepLaunch &fs);
+
 // small helper kernels (spectrum.cu)
 void fill_f32(float *dst, size_t n, float v, cudaStream_t s);
 // peaks[i] = max(accumulate ? peaks[i] : -999999, max_s partial[s][i])

@@ -13,6 +13,7 @@
 #include "../../rfanalyzer_b200/csrc/spectrum_kernel.cuh"
 #include "../../rfanalyzer_b200/csrc/spectrum2_kernel.cuh"
 #include "../../rfanalyzer_b200/csrc/spectrum64_kernel.cuh"
+#include "../../rfanalyzer_b200/csrc/fourstep_kernel.cuh"
 
 using namespace rfa;
 
@@ -231,6 +232,84 @@ extern "C" int emu_spectrum64(int in_fmt, int window_kind, const void *in, long 
         case FMT_U8: return emu_k64<FMT_U8>(in, window_kind, nframes, rows, peaks);
         case FMT_S16LE: return emu_k64<FMT_S16LE>(in, window_kind, nframes, rows, peaks);
     }
+    return -1;
+}
+
+// ---- four-step path (fourstep_kernel.cuh), N = 32768 / 65536: columns -> Z -> rows, thread by thread ----
+template <int N1, int IN>
+int emu_fourstep(const void *in, int window_kind, long long nframes, float *rows, float *peaks, long long store_from) {
+    using G = GeomFS<N1>;
+    using FA = FourStepA<N1, IN>;
+    using FB = FourStepB<N1>;
+    constexpr int N = G::N, T1 = G::T1, BPS = in_elem_bytes<IN>();
+    std::vector<cf> tw1 = make_pass_twiddles(N1), tw256 = make_pass_twiddles(256), twN(N);
+    make_twiddles(N, twN.data());
+    std::vector<float> win;
+    if (window_kind >= 0) {
+        win.resize(N);
+        make_window(window_kind, N, win.data());
+    }
+    const float bias = -3.0102999566398120f * log2f((float)N);
+    std::vector<cf> z((size_t)N), xcol(G::CSTRIDE), xrow(G::RSTRIDE);
+    std::vector<std::array<cf, 16>> U(T1 > 16 ? T1 : 16);
+    std::vector<std::array<float, 16>> PK((size_t)N1 * 16);  // [k1][t]
+    for (auto &a : PK) a.fill(-999999.0f);
+    for (long long f = 0; f < nframes; f++) {
+        const char *frame = (const char *)in + f * (long long)N * BPS;
+        for (int n2 = 0; n2 < 256; n2++) {
+            for (int t = 0; t < T1; t++) {
+                float wreg[16];
+                uint32_t raw[16];
+                FA::load_window(win.empty() ? nullptr : win.data(), n2, t, wreg);
+                FA::load_raw(frame + ((size_t)t * 256 + n2) * BPS, raw);
+                FA::first(raw, wreg, U[t].data());
+                FA::scatter(xcol.data(), t, U[t].data());
+            }
+            for (int t = 0; t < T1; t++) {
+                cf twreg[FA::NB * (FA::R1 - 1)], twz[16], u[16];
+                FA::load_pass_tw(tw1.data(), t, twreg);
+                FA::load_col_tw(twN.data(), n2, t, twz);
+                FA::second(xcol.data(), twreg, twz, t, u, z.data() + n2);
+            }
+        }
+        float *out = rows + f * (long long)N;
+        for (int k1 = 0; k1 < N1; k1++) {
+            for (int t = 0; t < 16; t++) {
+                FB::first(z.data() + (size_t)k1 * 256, t, U[t].data());
+                FB::scatter(xrow.data(), t, U[t].data());
+            }
+            for (int t = 0; t < 16; t++) {
+                cf twreg[15];
+                FB::load_pass_tw(tw256.data(), t, twreg);
+                float *pk = PK[(size_t)k1 * 16 + t].data();
+                if (f >= store_from)
+                    FB::template second<true, true>(xrow.data(), twreg, t, k1, out, pk, bias);
+                else
+                    FB::template second<true, false>(xrow.data(), twreg, t, k1, out, pk, bias);
+            }
+        }
+    }
+    if (peaks)
+        for (int k1 = 0; k1 < N1; k1++)
+            for (int t = 0; t < 16; t++)
+                for (int c = 0; c < 16; c++) peaks[FB::bin_of(t, k1, c)] = PK[(size_t)k1 * 16 + t][c];
+    return 0;
+}
+
+template <int N1>
+int emu_fourstep_fmt(int in_fmt, const void *in, int window_kind, long long nframes, float *rows, float *peaks, long long store_from) {
+    switch (in_fmt) {
+        case FMT_S8: return emu_fourstep<N1, FMT_S8>(in, window_kind, nframes, rows, peaks, store_from);
+        case FMT_U8: return emu_fourstep<N1, FMT_U8>(in, window_kind, nframes, rows, peaks, store_from);
+        case FMT_S16LE: return emu_fourstep<N1, FMT_S16LE>(in, window_kind, nframes, rows, peaks, store_from);
+    }
+    return -1;
+}
+
+extern "C" int emu_fourstep_spectrum(int N, int in_fmt, int window_kind, const void *in, long long nframes, float *rows,
+                                     float *peaks, long long store_from) {
+    if (N == 65536) return emu_fourstep_fmt<256>(in_fmt, in, window_kind, nframes, rows, peaks, store_from);
+    if (N == 32768) return emu_fourstep_fmt<128>(in_fmt, in, window_kind, nframes, rows, peaks, store_from);
     return -1;
 }
 

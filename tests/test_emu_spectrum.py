@@ -131,3 +131,31 @@ def test_k64_path_vs_oracle(emu, oracle, fmt):
     assert np.abs(peaks - p).max() < 0.01
     lin, lin_ref = 10.0 ** (rows / 5.0), 10.0 ** (r / 5.0)
     assert np.all(np.abs(lin - lin_ref) <= 1e-4 * lin_ref + 1e-6 * lin_ref.max())
+
+
+# ---- four-step path (fourstep_kernel.cuh): N = 32768 / 65536 as N1 x 256 through an intermediate buffer ----
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_fourstep_vs_oracle(emu, oracle, fmt, n):
+    frames = 2
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows = np.full((frames, n), 7.0, np.float32)
+    peaks = np.zeros(n, np.float32)
+    assert emu.emu_fourstep_spectrum(n, fmt, 0, iq.ctypes.data, frames, rows.ctypes.data, peaks.ctypes.data, 0) == 0
+    r, p, _ = oracle.spectrum_run(fmt, iq, n, 1)
+    assert np.abs(rows - r).max() < 0.01
+    assert np.abs(peaks - p).max() < 0.01
+    lin, lin_ref = 10.0 ** (rows / 5.0), 10.0 ** (r / 5.0)
+    assert np.all(np.abs(lin - lin_ref) <= 1e-4 * lin_ref + 1e-6 * lin_ref.max())
+
+
+def test_fourstep_store_from_keeps_older_rows_untouched(emu, oracle):
+    n, frames = 32768, 3
+    iq = oracle.synth_iq(0, n * frames)
+    rows = np.full((frames, n), 7.0, np.float32)
+    peaks = np.zeros(n, np.float32)
+    assert emu.emu_fourstep_spectrum(n, 0, 0, iq.ctypes.data, frames, rows.ctypes.data, peaks.ctypes.data, 2) == 0
+    r, p, _ = oracle.spectrum_run(0, iq, n, 1)
+    assert np.all(rows[:2] == 7.0)
+    assert np.abs(rows[2] - r[2]).max() < 0.01
+    assert np.abs(peaks - p).max() < 0.01      # peak hold still sees every frame

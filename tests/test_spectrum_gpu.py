@@ -342,3 +342,57 @@ def test_process_file_matches_the_in_memory_pass(gpu_ctx, oracle, tmp_path, fmt,
 def parse_name(ctx, path):
     import rfanalyzer_b200 as rfa
     return rfa.parse_recording_name(ctx, os.path.basename(path))
+
+
+# ---- four-step path (fourstep_kernel.cuh), N = 32768 / 65536 ----
+@pytest.mark.parametrize("fmt,n,frames,batch_kib", [(0, 65536, 7, 1024), (2, 32768, 9, 512), (1, 65536, 3, 0)])
+def test_fourstep_batches_ring_and_history(gpu_ctx, oracle, monkeypatch, fmt, n, frames, batch_kib):
+    """Several batches through a small intermediate buffer (RFA_FS_BATCH_KIB, read per call), rows into a
+    backwards ring with history, accumulating peaks, average over ring rows."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    L, ring = 4, 12
+    if batch_kib:
+        monkeypatch.setenv("RFA_FS_BATCH_KIB", str(batch_kib))
+    plan = rfa.SpectrumPlan(gpu_ctx, fmt, n, avg_len=L)
+    L_o = oracle.lib()
+    proc = L_o.orc_fftproc_new(ring, 1)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
+        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
+        write_index, history, first = 0, 0, 0
+        for call, fr in enumerate((frames, 2, 14)):
+            iq = oracle.synth_iq(fmt, n * fr, first=first)
+            first += n * fr
+            r, _, _ = oracle.spectrum_run(fmt, iq, n, 0)
+            for k in range(fr):
+                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
+            plan.process(torch.from_numpy(iq).cuda(), fr, rows=d_ring, peaks=d_peaks, avg=d_avg, row0=write_index,
+                         row_step=-1, ring_rows=ring, history_rows=history, peaks_accumulate=call > 0)
+            gpu_ctx.sync()
+            write_index = (write_index - fr) % ring
+            history = min(ring, history + fr)
+            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
+            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
+            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
+            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
+            avg_ref = np.empty(n, np.float32)
+            L_o.orc_time_average(proc, L, avg_ref)
+            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
+    L_o.orc_fftproc_free(proc)
+
+
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_fourstep_matches_the_residue_split_kernel(gpu_ctx, oracle, monkeypatch, n):
+    """Two factorisations of the same transform: fourstep_kernel.cuh vs spectrum_kernel's residue split
+    (RFA_FOURSTEP=0, read per call)."""
+    frames = 6
+    iq = oracle.synth_iq(0, n * frames)
+    rows4, peaks4, avg4 = gpu_spectrum(gpu_ctx, 0, iq, n, L=3)
+    monkeypatch.setenv("RFA_FOURSTEP", "0")
+    rows1, peaks1, avg1 = gpu_spectrum(gpu_ctx, 0, iq, n, L=3)
+    assert np.abs(rows4 - rows1).max() < DB_TOL
+    assert np.abs(peaks4 - peaks1).max() < DB_TOL
+    assert np.abs(avg4 - avg1).max() < DB_TOL
+    assert np.array_equal(rows4.argmax(axis=1), rows1.argmax(axis=1))
