@@ -41,9 +41,8 @@ struct GeomFS {
     static constexpr int GROUPS_B = N1 / 16;     // row groups of 16 rows (step B)
     static constexpr int CSTRIDE = (Plan<N1>::SMEM_POINTS | 1);   // odd: lanes = columns
     static constexpr int RSTRIDE = (Plan<256>::SMEM_POINTS | 1);  // odd: lanes = rows
-    static constexpr int TSTRIDE = 257;                           // staged Z tile, odd
     static constexpr size_t SMEM_A = (size_t)CPC * CSTRIDE * sizeof(cf);
-    static constexpr size_t SMEM_B = (size_t)16 * (RSTRIDE + TSTRIDE) * sizeof(cf);
+    static constexpr size_t SMEM_B = (size_t)(2 * 16 * 256 + 16 * RSTRIDE) * sizeof(cf);  // two dense Z tiles + exchange
     static_assert(N1 == 128 || N1 == 256, "four-step covers N = 32768 and 65536");
     static_assert(Plan<N1>::PASSES == 2 && Plan<256>::PASSES == 2, "two passes per step");
 };
@@ -182,40 +181,57 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
     }
 }
 
-// grid = GROUPS_B * lanes; CTA (group, lane) transforms rows 16*group .. 16*group+15 of its frames
+// grid = GROUPS_B * lanes; CTA (group, lane) transforms rows 16*group .. 16*group+15 of its frames.
+// The 16 rows are 32 KB of contiguous Z: ONE bulk copy (cp.async.bulk, mbarrier completion) brings them into a
+// two-deep ring of dense tiles, issued two frames ahead, so no thread ever waits on a global load of Z.  A thread
+// has two identities: in the first pass lanes are consecutive POINTS of a row (the dense tile is read 128 bytes at
+// a time), in the second pass lanes are consecutive ROWS (= consecutive bins k1: coalesced row stores); the
+// exchange buffer between the passes is where the identity changes.
 template <int N1>
 __global__ void __launch_bounds__(256) fourstep_rows_kernel(const FourStepParams a) {
     using G = GeomFS<N1>;
     using F = FourStepB<N1>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int row = threadIdx.x % 16, t = threadIdx.x / 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    const int row1 = threadIdx.x / 16, t1 = threadIdx.x % 16;  // first pass
+    const int row = threadIdx.x % 16, t = threadIdx.x / 16;    // second pass
     const int group = blockIdx.x % G::GROUPS_B, lane = blockIdx.x / G::GROUPS_B, lanes = gridDim.x / G::GROUPS_B;
     const int k1 = group * 16 + row;
-    cf *xs = reinterpret_cast<cf *>(smem_raw);             // [16][RSTRIDE] exchange
-    cf *tile = xs + 16 * G::RSTRIDE;                        // [16][TSTRIDE] staged rows of Z
+    constexpr int TILE = 16 * 256;                          // points per tile
+    cf *tile = reinterpret_cast<cf *>(smem_raw);           // [2][TILE] staged rows of Z, dense
+    cf *xs = tile + 2 * TILE;                               // [16][RSTRIDE] exchange
     cf twreg[15];
     launch_dependents();
     F::load_pass_tw(a.tw_256, t, twreg);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_mbar[0]);
+        mbar_init(&s_mbar[1]);
+    }
+    __syncthreads();
     grid_dependency_wait();
+    const cf *zg = a.z + (size_t)group * TILE;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+            if (lane + b * lanes < a.nbatch)
+                tma_load_1d(tile + b * TILE, zg + (size_t)(lane + b * lanes) * G::N, TILE * sizeof(cf), &s_mbar[b]);
+    }
     float pk[16];
 #pragma unroll
     for (int c = 0; c < 16; c++) pk[c] = -999999.0f;
     const bool want_peak = a.p.peaks != nullptr;
     bool worked = false;
-    for (int fb = lane; fb < a.nbatch; fb += lanes) {
+    int it = 0;
+    for (int fb = lane; fb < a.nbatch; fb += lanes, it++) {
         const long long f = a.frame0 + fb;
-        // stage the 16 rows (32 KB, contiguous in Z) with coalesced loads
-        const cf *zt = a.z + (size_t)fb * G::N + (size_t)group * 16 * 256;
-        __syncthreads();  // the previous frame's passes are done with both buffers
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const int idx = threadIdx.x + 256 * j;
-            tile[(idx >> 8) * G::TSTRIDE + (idx & 255)] = zt[idx];
-        }
-        __syncthreads();
+        const int b = it & 1;
+        mbar_wait(&s_mbar[b], (uint32_t)((it >> 1) & 1));
         cf u[16];
-        F::first(tile + row * G::TSTRIDE, t, u);
-        F::scatter(xs + row * G::RSTRIDE, t, u);
+        F::first(tile + b * TILE + row1 * 256, t1, u);
+        __syncthreads();  // the previous frame's second pass is done with xs; everybody has read tile b
+        if (threadIdx.x == 0 && fb + 2 * lanes < a.nbatch)
+            tma_load_1d(tile + b * TILE, zg + (size_t)(fb + 2 * lanes) * G::N, TILE * sizeof(cf), &s_mbar[b]);
+        F::scatter(xs + row1 * G::RSTRIDE, t1, u);
         __syncthreads();
         float *out = a.p.rows + frame_row(a.p, f) * a.p.row_stride;
         const cf *xrow = xs + row * G::RSTRIDE;
