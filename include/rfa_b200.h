@@ -155,6 +155,49 @@ int rfa_channel_strength(rfa_ctx *ctx, const float *rows, long long row0, long l
 /* FftProcessor.kt:199-217: shift `nrows` device rows by `shift` bins, fill with -9999f. */
 int rfa_shift_rows(rfa_ctx *ctx, float *rows, long long nrows, long long row_stride, int n, int shift);
 
+/* ---- signal detectors on waterfall rows --------------------------------------
+ * ui/MainViewModel.kt: getAverageSignalLevel (:1392-1414), detectSignal (:1416-1461), detectSignalsInFFT
+ * (:1463-1550), detectIEMChannelsInFFT (:861-935), detectAirCommSignal / ...AtFrequency (:1151-1250),
+ * groupSignals / finalizeGroup (:1552-1607); ScanDetectionMode ui/composable/ScanTab.kt:35-39.
+ * Every detector reduces windows of bins of a dB row to peak = windowData.maxOrNull() (NaN-propagating float
+ * max) and avg = windowData.average().toFloat() (double sum, one division, one rounding). */
+enum { RFA_DETECT_PEAK_ONLY = 0, RFA_DETECT_AVERAGE_ONLY = 1, RFA_DETECT_PEAK_OR_AVERAGE = 2 };
+typedef struct rfa_detect_window {
+    long long row; /* row index into `rows` (row * row_stride floats from the base) */
+    int start;     /* first bin, clamped to 0 */
+    int end;       /* last bin INCLUSIVE, clamped to n-1 (sliceArray(windowStart..windowEnd)) */
+} rfa_detect_window;
+typedef struct rfa_signal { /* DiscoveredSignal: frequency, peakStrength, averageStrength, bandwidth, isGrouped */
+    long long frequency;
+    float peak;
+    float average;
+    long long bandwidth;
+    int grouped;
+} rfa_signal;
+/* peak[i], avg[i] of window i over device-resident rows; windows per mem_win, outputs per mem_out.
+ * One launch for any number of (row, window) pairs: a batch of rows is scanned without leaving HBM. */
+int rfa_detect_windows(rfa_ctx *ctx, const float *rows, long long row_stride, int n, const rfa_detect_window *win,
+                       int nwin, float *peak, float *avg, int mem_win, int mem_out);
+/* host arithmetic of the detectors, with the JVM's conversions (Long -> Float, float division, toInt()):
+ * binIndex = ((freq - (center - fs/2)) / (fs.toFloat() / n)).toInt() */
+int rfa_detect_bin(long long center_freq, long long sample_rate, int n, long long freq);
+/* windowHalfSize = (half_width_hz / (fs.toFloat() / n)).toInt().coerceAtLeast(min_half) */
+int rfa_detect_half_width(long long sample_rate, int n, int half_width_hz, int min_half);
+/* bin and clamped window of `freq`; half_width_hz < 0 = a fixed +-min_half bins.  Returns 1 when the bin
+ * lies inside the row (`binIndex in currentFFT.indices`), 0 when the reference skips it. */
+int rfa_detect_window_at(long long center_freq, long long sample_rate, int n, long long freq, int half_width_hz,
+                         int min_half, int *bin, int *start, int *end);
+/* detection mode against maxOf(threshold, noiseFloor + noiseFloorMargin): 1 detected, 0 not, -1 bad mode */
+int rfa_detect_decide(float peak, float avg, float threshold, float noise_floor, float margin, int mode);
+/* the frequency grid of detectSignalsInFFT and its +-2-bin windows on row `row`; writes at most `cap` entries,
+ * returns the number of grid points inside the row (call with cap = 0 to size the arrays), -1 on bad input */
+long long rfa_scan_grid(long long center_freq, long long sample_rate, long long usable_bandwidth, long long step,
+                        long long scan_start, long long scan_end, int n, long long row, long long *freqs,
+                        rfa_detect_window *win, long long cap);
+/* groupSignals: sort by frequency, merge neighbours closer than step * minimum_gap; `out` holds up to n
+ * signals, the count is returned */
+long long rfa_group_signals(const rfa_signal *in, long long n, long long step, int minimum_gap, rfa_signal *out);
+
 /* ---- waterfall / FFT-trace preprocessing -------------------------------------
  * AnalyzerSurface.drawPreprocessing (ui/AnalyzerSurface.kt:646-734), arithmetic only: per pixel the mean of
  * the row's bins (:703-713), colour-map index int((avg-minDB)*mapSize/(maxDB-minDB)) clamped (:726-727),

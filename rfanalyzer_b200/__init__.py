@@ -13,6 +13,7 @@ from ._lib import (FMT_S8, FMT_U8, FMT_S16LE, WIN_BLACKMAN_REF, WIN_HANN, WIN_RE
 from .engine import Context, SpectrumPlan, synth_iq, synth_step, default_synth_components
 
 from . import dsp
+from . import detect
 from .dsp import (SamplePacket, Signed8BitIQConverter, Unsigned8BitIQConverter, Signed16BitIQConverter, NativeDsp,
                   FftProcessor, FftProcessorData, FirFilter, ComplexFirFilter, RationalResampler, Demodulator, AudioSink,
                   ChainPlan, FileIQSource, parse_recording_name, recording_file_name)

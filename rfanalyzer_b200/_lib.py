@@ -60,6 +60,19 @@ class ChainDesc(C.Structure):
                 ("packet_samples", C.c_int), ("volume", C.c_float), ("flags", C.c_int)]
 
 
+class DetectWindow(C.Structure):
+    """rfa_detect_window: (row, first bin, last bin inclusive)."""
+    _fields_ = [("row", C.c_longlong), ("start", C.c_int), ("end", C.c_int)]
+
+
+class Signal(C.Structure):
+    """rfa_signal: DiscoveredSignal's numeric fields."""
+    _fields_ = [("frequency", C.c_longlong), ("peak", C.c_float), ("average", C.c_float), ("bandwidth", C.c_longlong),
+                ("grouped", C.c_int)]
+
+
+DETECT_PEAK_ONLY, DETECT_AVERAGE_ONLY, DETECT_PEAK_OR_AVERAGE = 0, 1, 2
+
 _vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 _pi, _pll, _pvp = C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_void_p)
 
@@ -92,6 +105,13 @@ SIGNATURES = {
     "rfa_channel_bins": (_i, [_i, _ll, _i, _ll, _ll, _pi, _pi]),
     "rfa_channel_strength": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _vp, _i]),
     "rfa_shift_rows": (_i, [_vp, _vp, _ll, _ll, _i, _i]),
+    "rfa_detect_windows": (_i, [_vp, _vp, _ll, _i, _vp, _i, _vp, _vp, _i, _i]),
+    "rfa_detect_bin": (_i, [_ll, _ll, _i, _ll]),
+    "rfa_detect_half_width": (_i, [_ll, _i, _i, _i]),
+    "rfa_detect_window_at": (_i, [_ll, _ll, _i, _ll, _i, _i, _pi, _pi, _pi]),
+    "rfa_detect_decide": (_i, [_f, _f, _f, _f, _f, _i]),
+    "rfa_scan_grid": (_ll, [_ll, _ll, _ll, _ll, _ll, _ll, _i, _ll, _vp, _vp, _ll]),
+    "rfa_group_signals": (_ll, [_vp, _ll, _ll, _i, _vp]),
     "rfa_fill": (_i, [_vp, _vp, _ll, _f]),
     "rfa_tap_window": (_i, [_i, _d, _i, _i, C.POINTER(C.c_float)]),
     "rfa_design_lowpass": (_i, [_f, _f, _f, _f, _f, _i, _d, _i, _vp, _i, _pi]),

@@ -110,6 +110,18 @@ class Context:
         check(self.lib.rfa_channel_strength(self.handle, ptr(rows), int(row0), int(row_step), int(ring_rows),
                                             int(row_stride), int(nrows), int(b0), int(b1), ptr(out), _mem_of(out)))
 
+    def detect_windows(self, rows, row_stride, n, windows, peak=None, avg=None):
+        """(peak, avg) of every (row, start, end) window over device rows (rfa_detect_windows).  `windows` is a
+        sequence of triples or a ctypes array of DetectWindow; outputs default to new host arrays."""
+        if not isinstance(windows, C.Array):
+            windows = (_lib.DetectWindow * len(windows))(*[_lib.DetectWindow(int(r), int(a), int(b)) for r, a, b in windows])
+        nwin = len(windows)
+        if peak is None:
+            peak, avg = np.empty(nwin, np.float32), np.empty(nwin, np.float32)
+        check(self.lib.rfa_detect_windows(self.handle, ptr(rows), int(row_stride), int(n), C.addressof(windows), nwin,
+                                          ptr(peak), ptr(avg), _lib.MEM_HOST, _mem_of(peak, avg)))
+        return peak, avg
+
     def shift_rows(self, rows, nrows, row_stride, n, shift):
         check(self.lib.rfa_shift_rows(self.handle, ptr(rows), int(nrows), int(row_stride), int(n), int(shift)))
 
