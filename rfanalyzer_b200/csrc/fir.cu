@@ -147,99 +147,76 @@ struct ResampleFastArgs {
     int bank_smem;  // bank floats copied to shared memory (0 = read through L1)
 };
 
-// four consecutive stream samples k .. k+3 (k >= 0, k % 4 == 0): raw words first (so that several
-// groups' loads are in flight before any is converted), then conversion + NCO mixing
-struct Raw4 {
-    uint4 w;    // raw codes (8-bit kinds use x, y) or, for planar floats, the four re values
-    float4 im;  // planar floats: the four im values
-};
+// one stream sample k >= 0: raw word first (so that several loads are in flight before any is converted)
 template <int KIND>
-__device__ __forceinline__ Raw4 load4(const StreamSrc &s, long long k) {
-    Raw4 r;
+__device__ __forceinline__ void load1(const StreamSrc &s, long long k, uint32_t &raw, float &im) {
     if (KIND == FMT_S8 || KIND == FMT_U8) {
-        const uint2 w = __ldg(reinterpret_cast<const uint2 *>((const char *)s.raw + k * 2));
-        r.w = make_uint4(w.x, w.y, 0u, 0u);
+        raw = (uint32_t)__ldg((const uint16_t *)s.raw + k);
     } else if (KIND == FMT_S16LE) {
-        r.w = __ldg(reinterpret_cast<const uint4 *>((const char *)s.raw + k * 4));
+        raw = __ldg((const uint32_t *)s.raw + k);
     } else {
-        r.w = make_uint4(__float_as_uint(s.re[k]), __float_as_uint(s.re[k + 1]), __float_as_uint(s.re[k + 2]),
-                         __float_as_uint(s.re[k + 3]));
-        r.im = s.im ? make_float4(s.im[k], s.im[k + 1], s.im[k + 2], s.im[k + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    return r;
-}
-template <int KIND>
-__device__ __forceinline__ void convert4(const StreamSrc &s, const Raw4 &raw, int t, float2 *dst) {
-    float r[4], q[4];
-    if (KIND == FMT_S8 || KIND == FMT_U8) {
-        const uint32_t c[4] = {raw.w.x & 0xFFFFu, raw.w.x >> 16, raw.w.y & 0xFFFFu, raw.w.y >> 16};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (KIND == FMT_S8) {
-                r[i] = conv_s8((int)(int8_t)(c[i] & 0xFF));
-                q[i] = conv_s8((int)(int8_t)(c[i] >> 8));
-            } else {
-                r[i] = conv_u8((int)(c[i] & 0xFF));
-                q[i] = conv_u8((int)(c[i] >> 8));
-            }
-        }
-    } else if (KIND == FMT_S16LE) {
-        const uint32_t c[4] = {raw.w.x, raw.w.y, raw.w.z, raw.w.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            r[i] = conv_s16((int)(int16_t)(c[i] & 0xFFFF));
-            q[i] = conv_s16((int)(int16_t)(c[i] >> 16));
-        }
-    } else {
-        r[0] = __uint_as_float(raw.w.x), r[1] = __uint_as_float(raw.w.y), r[2] = __uint_as_float(raw.w.z),
-        r[3] = __uint_as_float(raw.w.w);
-        q[0] = raw.im.x, q[1] = raw.im.y, q[2] = raw.im.z, q[3] = raw.im.w;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        if (KIND != 3 && s.nco_cos) {
-            int ti = t + i;
-            while (ti >= s.nco_len) ti -= s.nco_len;
-            const float c = __ldg(s.nco_cos + ti), sn = __ldg(s.nco_sin + ti);
-            dst[i] = make_float2(__fsub_rn(__fmul_rn(r[i], c), __fmul_rn(q[i], sn)),
-                                 __fadd_rn(__fmul_rn(q[i], c), __fmul_rn(r[i], sn)));
-        } else {
-            dst[i] = make_float2(r[i], q[i]);
-        }
+        raw = __float_as_uint(s.re[k]);
+        im = s.im ? s.im[k] : 0.0f;
     }
 }
-
+// ... then conversion + NCO mixing; t = NCO table index of the sample
+template <int KIND>
+__device__ __forceinline__ float2 convert1(const StreamSrc &s, uint32_t raw, float im, int t) {
+    float r, q;
+    if (KIND == FMT_S8) {
+        r = conv_s8((int)(int8_t)(raw & 0xFF));
+        q = conv_s8((int)(int8_t)(raw >> 8));
+    } else if (KIND == FMT_U8) {
+        r = conv_u8((int)(raw & 0xFF));
+        q = conv_u8((int)(raw >> 8));
+    } else if (KIND == FMT_S16LE) {
+        r = conv_s16((int)(int16_t)(raw & 0xFFFF));
+        q = conv_s16((int)(int16_t)(raw >> 16));
+    } else {
+        r = __uint_as_float(raw);
+        q = im;
+    }
+    if (KIND != 3 && s.nco_cos) {  // Signed8BitIQConverter.java:119-120: four rounded products, then -/+
+        const float c = __ldg(s.nco_cos + t), sn = __ldg(s.nco_sin + t);
+        return make_float2(__fsub_rn(__fmul_rn(r, c), __fmul_rn(q, sn)), __fadd_rn(__fmul_rn(q, c), __fmul_rn(r, sn)));
+    }
+    return make_float2(r, q);
+}
+// Stage samples [k_al, k_al + span) of the stream into xs[0 .. span).  Consecutive lanes take consecutive
+// samples: the raw loads, the NCO table reads and the 64-bit shared-memory stores are all stride-1 across a
+// warp (four consecutive samples per thread cost a 4-way bank conflict on every store, four cache lines per
+// table read and a wrap-around loop per sample).
 template <int KIND>
 __device__ __forceinline__ void stage_span(const StreamSrc &src, long long k_al, int span, float2 *xs) {
     const int nco_len = src.nco_len > 0 ? src.nco_len : 1;
-    // NCO index of sample k_al + 4*threadIdx.x, then advanced by 4*blockDim.x per group
-    long long t0 = ((long long)src.nco_idx + k_al + 4LL * threadIdx.x) % nco_len;
+    // NCO index of sample k_al + threadIdx.x, then advanced by blockDim.x per round
+    long long t0 = ((long long)src.nco_idx + k_al + threadIdx.x) % nco_len;
     if (t0 < 0) t0 += nco_len;
     int t = (int)t0;
-    const int tstep = (int)((4LL * blockDim.x) % nco_len), sstep = 4 * (int)blockDim.x;
-    constexpr int U = 4;  // groups in flight per thread: the staging is a chain of DRAM round trips otherwise
-    for (int s0 = 4 * threadIdx.x; s0 < span; s0 += U * sstep) {
-        Raw4 raw[U];
-        bool fast[U];
+    const int sstep = (int)blockDim.x, tstep = sstep % nco_len;
+    constexpr int U = 8;  // loads in flight per thread: the staging is a chain of DRAM round trips otherwise
+    for (int s0 = threadIdx.x; s0 < span; s0 += U * sstep) {
+        uint32_t raw[U];
+        float rim[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int sidx = s0 + u * sstep;
             const long long k = k_al + sidx;
-            fast[u] = sidx + 3 < span && k >= 0;
-            if (fast[u]) raw[u] = load4<KIND>(src, k);
+            rim[u] = 0.0f;
+            raw[u] = 0u;
+            if (sidx < span && k >= 0) load1<KIND>(src, k, raw[u], rim[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int sidx = s0 + u * sstep;
-            if (fast[u]) {
-                convert4<KIND>(src, raw[u], t, xs + sidx);
-            } else if (sidx < span) {  // history (and the zeros before it), the last samples of the span
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (sidx + i >= span) break;
+            const long long k = k_al + sidx;
+            if (sidx < span) {
+                if (k >= 0) {
+                    xs[sidx] = convert1<KIND>(src, raw[u], rim[u], t);
+                } else {  // history (and the zeros before it)
                     float r, q;
-                    fetch<KIND>(src, k_al + sidx + i, r, q);
-                    xs[sidx + i] = make_float2(r, q);
+                    fetch<KIND>(src, k, r, q);
+                    xs[sidx] = make_float2(r, q);
                 }
             }
             t += tstep;
@@ -247,7 +224,6 @@ __device__ __forceinline__ void stage_span(const StreamSrc &src, long long k_al,
         }
     }
 }
-
 template <int KIND, bool BANK_SMEM, int G>
 __global__ void __launch_bounds__(256) resample_fast_kernel(const ResampleFastArgs fa) {
     const ResampleArgs &a = fa.a;
@@ -510,7 +486,7 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
     a.out_im = out_im;
     const unsigned grid = (unsigned)((nout + tile - 1) / tile);
     const size_t smem = 2 * (size_t)kSpanMax * sizeof(float);
-    const bool aligned = in.kind == 3 || ((size_t)in.raw & 15) == 0;  // the fast paths load 64/128-bit groups
+    const bool aligned = in.kind == 3 || ((size_t)in.raw & (in.kind == 2 ? 3 : 1)) == 0;  // one IQ pair per load
     const int A = (nt + D - 1) / D;
     if (!exact && aligned && A >= 2 && A <= 12 && (size_t)I * D * 12 <= 8192) {
         // register-tiled path: M = 9 outputs per thread, B blocks per phase
