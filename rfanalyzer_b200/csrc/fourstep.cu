@@ -1,5 +1,6 @@
 // fourstep.cu -- launcher of the four-step spectrum path (fourstep_kernel.cuh) for N = 32768, 65536.
 #include <stdlib.h>
+#include <string.h>
 
 #include "fourstep_kernel.cuh"
 #include "spectrum_launch.h"
@@ -19,22 +20,59 @@ cudaError_t resident_ctas(K kern, size_t smem, int *occ) {
     return e;
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// the IQ bytes of a call as a [frames * N1][256 * bps] byte matrix, box = one column group of one frame
+template <int N1>
+bool make_input_map(const void *iq, long long nframes, int bps, CUtensorMap *tm) {
+    using G = GeomFS<N1>;
+    const char *e = getenv("RFA_FS_TMA");  // RFA_FS_TMA=0: per-thread loads (A/B timing runs, the fallback's test)
+    if (e && atoi(e) == 0) return false;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || ((size_t)iq & 15) != 0 || nframes * N1 > 0xFFFFFFFFLL) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)256 * bps, (cuuint64_t)nframes * N1};
+    const cuuint64_t strides[1] = {(cuuint64_t)256 * bps};
+    const cuuint32_t box[2] = {(cuuint32_t)(G::CPC * bps), (cuuint32_t)N1};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(iq), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int N1, int IN>
 cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     using G = GeomFS<N1>;
-    auto ka = fourstep_cols_kernel<N1, IN>;
+    constexpr int BPS = in_elem_bytes<IN>();
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const bool staged = make_input_map<N1>(L.p.in, L.p.nframes, BPS, &tmap);
+    auto ka = staged ? fourstep_cols_kernel<N1, IN, true> : fourstep_cols_kernel<N1, IN, false>;
     auto kb = fourstep_rows_kernel<N1>;
-    static thread_local int dev_done = -1, occ_a = 1, occ_b = 1;  // per instantiation <N1, IN>, per device
+    const size_t smem_a = staged ? G::smem_a_staged(BPS) : G::SMEM_A;
+    static thread_local int dev_done[2] = {-1, -1}, occ_as[2] = {1, 1}, occ_b = 1;  // per instantiation <N1, IN>, per device
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev_done != dev) {
-        e = resident_ctas(ka, G::SMEM_A, &occ_a);
+    if (dev_done[staged] != dev) {
+        e = resident_ctas(ka, smem_a, &occ_as[staged]);
         if (e != cudaSuccess) return e;
         e = resident_ctas(kb, G::SMEM_B, &occ_b);
         if (e != cudaSuccess) return e;
-        dev_done = dev;
+        dev_done[staged] = dev;
     }
+    const int occ_a = occ_as[staged];
     const long long batch = fs.z_bytes / ((long long)G::N * (long long)sizeof(cf));
     if (batch < 1) return cudaErrorInvalidValue;
     const char *ep = getenv("RFA_FS_PDL");  // RFA_FS_PDL=0: plain stream order (A/B timing runs)
@@ -65,8 +103,8 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cfg.gridDim = dim3((unsigned)(lanes_a * G::GROUPS_A));
-        cfg.dynamicSmemBytes = G::SMEM_A;
-        e = cudaLaunchKernelEx(&cfg, ka, a);
+        cfg.dynamicSmemBytes = smem_a;
+        e = cudaLaunchKernelEx(&cfg, ka, a, tmap);
         if (e != cudaSuccess) return e;
         cfg.gridDim = dim3((unsigned)(lanes_b * G::GROUPS_B));
         cfg.dynamicSmemBytes = G::SMEM_B;

@@ -19,6 +19,9 @@
 // column (row) group for the whole launch: window taps, twiddles and running peaks stay in registers.
 #pragma once
 #include "spectrum_kernel.cuh"
+#ifdef __CUDACC__
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 
 namespace rfa {
 
@@ -42,6 +45,10 @@ struct GeomFS {
     static constexpr int CSTRIDE = (Plan<N1>::SMEM_POINTS | 1);   // odd: lanes = columns
     static constexpr int RSTRIDE = (Plan<256>::SMEM_POINTS | 1);  // odd: lanes = rows
     static constexpr size_t SMEM_A = (size_t)CPC * CSTRIDE * sizeof(cf);
+    // staged variant: two raw tiles [N1][CPC] of b-byte IQ pairs behind the exchange buffers (128-byte aligned)
+    static constexpr size_t XCHG_A = (SMEM_A + 127) / 128 * 128;
+    static RFA_CX size_t tile_bytes(int bps) { return (size_t)N1 * CPC * bps; }
+    static RFA_CX size_t smem_a_staged(int bps) { return XCHG_A + 2 * tile_bytes(bps); }
     static constexpr size_t SMEM_B = (size_t)(2 * 16 * 256 + 16 * RSTRIDE) * sizeof(cf);  // two dense Z tiles + exchange
     static_assert(N1 == 128 || N1 == 256, "four-step covers N = 32768 and 65536");
     static_assert(Plan<N1>::PASSES == 2 && Plan<256>::PASSES == 2, "two passes per step");
@@ -57,6 +64,14 @@ struct FourStepA {
 #pragma unroll
         for (int r = 0; r < 16; r++)
             raw[r] = (IN == FMT_S16LE) ? ((const uint32_t *)src)[(size_t)r * T1 * 256] : (uint32_t)((const uint16_t *)src)[(size_t)r * T1 * 256];
+    }
+    // the same codes from a staged tile [N1 rows][CPC columns] of raw IQ pairs (the TMA box of this column group)
+    static RFA_HD void load_raw_tile(const void *tile, int col, int t, uint32_t *raw) {
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int i = (t + r * T1) * G::CPC + col;
+            raw[r] = (IN == FMT_S16LE) ? ((const uint32_t *)tile)[i] : (uint32_t)((const uint16_t *)tile)[i];
+        }
     }
     static RFA_HD void load_window(const float *win, int n2, int t, float *wreg) {
 #pragma unroll
@@ -148,17 +163,33 @@ struct FourStepB {
 __device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// 2-D tiled bulk copy (TMA): box {c0 .. , c1 ..} of the tensor map into shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint32_t bytes, unsigned long long *mbar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(mbar))
+                 : "memory");
+}
+
 // grid = GROUPS_A * lanes; CTA (group, lane) transforms column group `group` of frames lane, lane+lanes, ...
-template <int N1, int IN>
-__global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(const FourStepParams a) {
+// STAGED: the column group's raw IQ -- N1 rows of CPC pairs, 512 (1024) bytes apart in the frame -- arrives as ONE
+// tensor-map box per frame in a two-deep ring (the per-thread version issues 16 two-byte loads per frame and
+// stalls on the load/store queue: ncu lg_throttle 2.0, gpurun_out/prof_fs1).  `tmap_in` views the IQ bytes of the
+// call as [frames * N1][256 * bytes-per-pair] uint8.
+template <int N1, int IN, bool STAGED>
+__global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(const FourStepParams a, const __grid_constant__ CUtensorMap tmap_in) {
     using G = GeomFS<N1>;
     using F = FourStepA<N1, IN>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
     const int col = threadIdx.x % G::CPC, t = threadIdx.x / G::CPC;
     const int group = blockIdx.x % G::GROUPS_A, lane = blockIdx.x / G::GROUPS_A, lanes = gridDim.x / G::GROUPS_A;
     const int n2 = group * G::CPC + col;
     cf *xcol = reinterpret_cast<cf *>(smem_raw) + (size_t)col * G::CSTRIDE;
     constexpr int BPS = in_elem_bytes<IN>();
+    constexpr uint32_t TILE_BYTES = (uint32_t)G::tile_bytes(BPS);
+    unsigned char *tiles = smem_raw + G::XCHG_A;  // [2][TILE_BYTES] (STAGED)
     float wreg[16];
     cf twreg[F::NB * (F::R1 - 1)], twz[16], u[16];
     uint32_t raw[16];
@@ -168,13 +199,42 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
     F::load_window(a.p.win, n2, t, wreg);
     F::load_pass_tw(a.tw_n1, t, twreg);
     F::load_col_tw(a.tw_n, n2, t, twz);
+    if constexpr (STAGED) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_mbar[0]);
+            mbar_init(&s_mbar[1]);
+        }
+        __syncthreads();
+    }
     grid_dependency_wait();
     const char *src0 = (const char *)a.p.in + ((size_t)t * 256 + n2) * BPS;
-    if (lane < a.nbatch) F::load_raw(src0 + (a.frame0 + lane) * (long long)G::N * BPS, raw);
-    for (int fb = lane; fb < a.nbatch; fb += lanes) {
-        F::first(raw, wreg, u);
-        if (fb + lanes < a.nbatch) F::load_raw(src0 + (a.frame0 + fb + lanes) * (long long)G::N * BPS, raw);
-        __syncthreads();  // the previous frame's second pass has read the exchange buffer
+    if constexpr (STAGED) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+                if (lane + b * lanes < a.nbatch)
+                    tma_load_2d(tiles + b * TILE_BYTES, &tmap_in, group * G::CPC * BPS, (int)((a.frame0 + lane + b * lanes) * N1),
+                                TILE_BYTES, &s_mbar[b]);
+        }
+    } else {
+        if (lane < a.nbatch) F::load_raw(src0 + (a.frame0 + lane) * (long long)G::N * BPS, raw);
+    }
+    int it = 0;
+    for (int fb = lane; fb < a.nbatch; fb += lanes, it++) {
+        if constexpr (STAGED) {
+            const int b = it & 1;
+            mbar_wait(&s_mbar[b], (uint32_t)((it >> 1) & 1));
+            F::load_raw_tile(tiles + b * TILE_BYTES, col, t, raw);
+            F::first(raw, wreg, u);
+            __syncthreads();  // the previous frame's second pass has read the exchange buffer; tile b is consumed
+            if (threadIdx.x == 0 && fb + 2 * lanes < a.nbatch)
+                tma_load_2d(tiles + b * TILE_BYTES, &tmap_in, group * G::CPC * BPS, (int)((a.frame0 + fb + 2 * lanes) * N1), TILE_BYTES,
+                            &s_mbar[b]);
+        } else {
+            F::first(raw, wreg, u);
+            if (fb + lanes < a.nbatch) F::load_raw(src0 + (a.frame0 + fb + lanes) * (long long)G::N * BPS, raw);
+            __syncthreads();  // the previous frame's second pass has read the exchange buffer
+        }
         F::scatter(xcol, t, u);
         __syncthreads();
         F::second(xcol, twreg, twz, t, u, a.z + (size_t)fb * G::N + n2);

@@ -396,3 +396,27 @@ def test_fourstep_matches_the_residue_split_kernel(gpu_ctx, oracle, monkeypatch,
     assert np.abs(peaks4 - peaks1).max() < DB_TOL
     assert np.abs(avg4 - avg1).max() < DB_TOL
     assert np.array_equal(rows4.argmax(axis=1), rows1.argmax(axis=1))
+
+
+@pytest.mark.parametrize("fmt,n", [(0, 65536), (1, 32768), (2, 65536), (2, 32768)])
+def test_fourstep_tensor_map_staging_equals_per_thread_loads(gpu_ctx, oracle, monkeypatch, fmt, n):
+    """The column kernel reads its raw IQ either through a 2-D tensor-map box per frame (default, 16-byte aligned
+    input) or with per-thread loads (RFA_FS_TMA=0, and any misaligned input): same arithmetic, identical rows."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    frames = 5
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows_t, peaks_t, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
+    monkeypatch.setenv("RFA_FS_TMA", "0")
+    rows_l, peaks_l, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
+    monkeypatch.delenv("RFA_FS_TMA")
+    assert np.array_equal(rows_t, rows_l) and np.array_equal(peaks_t, peaks_l)
+    # an input that starts 4 bytes into an allocation is not 16-byte aligned: the launcher must fall back by itself
+    plan = rfa.SpectrumPlan(gpu_ctx, fmt, n)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        buf = torch.zeros(len(iq.view(np.uint8)) + 4, dtype=torch.uint8, device="cuda")
+        buf[4:] = torch.from_numpy(iq.view(np.uint8)).cuda()
+        rows_m = torch.zeros((frames, n), dtype=torch.float32, device="cuda")
+        plan.process(buf[4:], frames, rows=rows_m)
+        gpu_ctx.sync()
+    assert np.array_equal(rows_m.cpu().numpy(), rows_t)
