@@ -358,6 +358,7 @@ struct rfa_spectrum_plan {
     const float *win = nullptr;
     Buf ticket;     // finished-tail-row counters of the fused kernel
     Buf zbuf;       // four-step intermediate (N >= 32768)
+    Buf fsync;      // four-step fused launch: per-frame hand-over counters
     Buf tail;       // (L+1) rows when the caller stores no rows
     Buf dpeaks;     // device running peaks (host mode)
     Buf davg;       // device average (host mode)
@@ -422,6 +423,8 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
         if (want > all) want = all;
         if (want < (long long)n * (long long)sizeof(cf)) want = (long long)n * (long long)sizeof(cf);
         if (int rc = pl->zbuf.ensure((size_t)want)) return rc;
+        if (int rc = pl->fsync.ensure(2 * (size_t)nframes * sizeof(unsigned int))) return rc;
+        fs.sync = pl->fsync.as<unsigned int>();
         fs.z = pl->zbuf.as<cf>();
         fs.z_bytes = want;
         cudaError_t e4 = fourstep_launch(L, fs);
@@ -483,6 +486,7 @@ int rfa_spectrum_plan_destroy(rfa_spectrum_plan *pl) {
     pl->tail.release();
     pl->ticket.release();
     pl->zbuf.release();
+    pl->fsync.release();
     pl->dpeaks.release();
     pl->davg.release();
     for (int i = 0; i < 2; i++) {

@@ -51,6 +51,70 @@ bool make_input_map(const void *iq, long long nframes, int bps, CUtensorMap *tm)
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+thread_local int g_last_launches = 0;
+
+// One cooperative launch for the whole call (fourstep_fused_kernel).  Returns cudaErrorNotSupported when the
+// configuration does not allow it; the caller then runs the two-kernel path.
+template <int N1, int IN>
+cudaError_t run_fused(const SpectrumLaunch &L, const FourStepLaunch &fs, const CUtensorMap &tmap) {
+    using G = GeomFS<N1>;
+    constexpr int BPS = in_elem_bytes<IN>();
+    // RFA_FS_FUSED=1 selects this path.  Measured on B200 it is correct but SLOWER than two kernels per batch
+    // (2^24 samples: 119 / 125 us against 77 / 81 us, gpurun_out/fs_timing5.log), so it is not the default.
+    const char *ef = getenv("RFA_FS_FUSED");
+    if (!(ef && atoi(ef) == 1) || !fs.sync || L.p.nframes > 0x7FFFFFFFLL) return cudaErrorNotSupported;
+    auto kf = fourstep_fused_kernel<N1, IN>;
+    const size_t smem = G::smem_fused(BPS);
+    static thread_local int dev_done = -1, occ = 0, coop = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev_done != dev) {
+        e = resident_ctas(kf, smem, &occ);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (e != cudaSuccess) return e;
+        dev_done = dev;
+    }
+    // one producer and one consumer CTA per SM, rounded down to whole lanes
+    const int lanes_a = L.num_sms / G::GROUPS_A, lanes_b = L.num_sms / G::GROUPS_B;
+    if (!coop || occ < 2 || lanes_a < 1 || lanes_b < 1) return cudaErrorNotSupported;
+    const char *er = getenv("RFA_FS_RING_KIB");  // Z ring size (tuning runs); default 32 MiB: a quarter of the L2
+    const long long ring_bytes = (long long)(er && atoi(er) > 0 ? atoi(er) : 32 << 10) << 10;
+    long long ring = ring_bytes / ((long long)G::N * (long long)sizeof(cf));
+    const long long min_ring = 2LL * lanes_b + lanes_a + 8;  // the consumers' look-ahead must stay inside the ring
+    if (ring < min_ring) ring = min_ring;
+    if (ring > L.p.nframes) ring = L.p.nframes;
+    if (ring * (long long)G::N * (long long)sizeof(cf) > fs.z_bytes) return cudaErrorNotSupported;
+    FourStepParams a{};
+    a.p = L.p;
+    a.tw_n1 = fs.tw_n1;
+    a.tw_256 = fs.tw_256;
+    a.tw_n = fs.tw_n;
+    a.z = fs.z;
+    a.frame0 = 0;
+    a.nbatch = (int)L.p.nframes;
+    a.ring = (int)ring;
+    a.n_prod = lanes_a * G::GROUPS_A;
+    a.col_done = fs.sync;
+    a.row_done = fs.sync + L.p.nframes;
+    e = cudaMemsetAsync(fs.sync, 0, 2 * (size_t)L.p.nframes * sizeof(unsigned int), L.stream);
+    if (e != cudaSuccess) return e;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(256);
+    cfg.gridDim = dim3((unsigned)(a.n_prod + lanes_b * G::GROUPS_B));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = L.stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kf, a, tmap);
+    if (e == cudaSuccess) g_last_launches = 1;
+    return e;
+}
+
 template <int N1, int IN>
 cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     using G = GeomFS<N1>;
@@ -61,6 +125,11 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     auto ka = staged ? fourstep_cols_kernel<N1, IN, true> : fourstep_cols_kernel<N1, IN, false>;
     auto kb = fourstep_rows_kernel<N1>;
     const size_t smem_a = staged ? G::smem_a_staged(BPS) : G::SMEM_A;
+    if (staged) {
+        const cudaError_t ef = run_fused<N1, IN>(L, fs, tmap);
+        if (ef != cudaErrorNotSupported) return ef;
+    }
+    g_last_launches = 0;
     static thread_local int dev_done[2] = {-1, -1}, occ_as[2] = {1, 1}, occ_b = 1;  // per instantiation <N1, IN>, per device
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -83,6 +152,7 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     a.tw_256 = fs.tw_256;
     a.tw_n = fs.tw_n;
     a.z = fs.z;
+    a.ring = 0x7FFFFFFF;
     for (long long f0 = 0; f0 < L.p.nframes; f0 += batch) {
         const long long nb = L.p.nframes - f0 < batch ? L.p.nframes - f0 : batch;
         a.frame0 = f0;
@@ -110,6 +180,7 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
         cfg.dynamicSmemBytes = G::SMEM_B;
         e = cudaLaunchKernelEx(&cfg, kb, a);
         if (e != cudaSuccess) return e;
+        g_last_launches += 2;
     }
     return cudaSuccess;
 }
@@ -132,10 +203,7 @@ bool fourstep_supported(int N, int in_fmt, int out_kind) {
     return (N == 32768 || N == 65536) && out_kind == OUT_DB && (in_fmt == FMT_S8 || in_fmt == FMT_U8 || in_fmt == FMT_S16LE);
 }
 
-int fourstep_launches(int N, long long nframes, long long z_bytes) {
-    const long long batch = z_bytes / ((long long)N * (long long)sizeof(cf));
-    return batch < 1 ? 0 : (int)(2 * ((nframes + batch - 1) / batch));
-}
+int fourstep_launches(int, long long, long long) { return g_last_launches; }
 
 cudaError_t fourstep_launch(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     if (L.p.nframes <= 0) return cudaSuccess;

@@ -33,6 +33,11 @@ struct FourStepParams {
     cf *z;                 // [batch][N1][256]
     long long frame0;      // first frame of this batch
     int nbatch;            // frames in this batch
+    // fused producer/consumer launch (fourstep_fused_kernel): Z is a ring of `ring` frames
+    int ring;              // frames in z (two-kernel path: >= nbatch)
+    int n_prod;            // CTAs 0 .. n_prod-1 transform columns, the rest rows
+    unsigned int *col_done;  // [nbatch] column groups finished per frame (zeroed before the launch)
+    unsigned int *row_done;  // [nbatch] row groups finished per frame
 };
 
 template <int N1>
@@ -50,6 +55,7 @@ struct GeomFS {
     static RFA_CX size_t tile_bytes(int bps) { return (size_t)N1 * CPC * bps; }
     static RFA_CX size_t smem_a_staged(int bps) { return XCHG_A + 2 * tile_bytes(bps); }
     static constexpr size_t SMEM_B = (size_t)(2 * 16 * 256 + 16 * RSTRIDE) * sizeof(cf);  // two dense Z tiles + exchange
+    static RFA_CX size_t smem_fused(int bps) { return smem_a_staged(bps) > SMEM_B ? smem_a_staged(bps) : SMEM_B; }
     static_assert(N1 == 128 || N1 == 256, "four-step covers N = 32768 and 65536");
     static_assert(Plan<N1>::PASSES == 2 && Plan<256>::PASSES == 2, "two passes per step");
 };
@@ -177,14 +183,36 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0,
 // tensor-map box per frame in a two-deep ring (the per-thread version issues 16 two-byte loads per frame and
 // stalls on the load/store queue: ncu lg_throttle 2.0, gpurun_out/prof_fs1).  `tmap_in` views the IQ bytes of the
 // call as [frames * N1][256 * bytes-per-pair] uint8.
-template <int N1, int IN, bool STAGED>
-__global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(const FourStepParams a, const __grid_constant__ CUtensorMap tmap_in) {
+// cross-CTA hand-over of the fused launch: a frame's counter is bumped once per finished group, after a CTA
+// barrier and a device-scope fence (the stores of all 256 threads are then visible to whoever acquires the count)
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_count(const unsigned int *p, unsigned int want) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(p) < want) {
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a lost hand-over must fail loudly, not hang the GPU
+    }
+}
+__device__ __forceinline__ void publish_count(unsigned int *p) {  // call by ONE thread after a CTA barrier
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");  // the consumer reads Z through the async proxy (TMA)
+    atomicAdd(p, 1u);
+}
+
+// One CTA of step A: column group bid % GROUPS_A of frames bid / GROUPS_A, + lanes, ...
+// FUSED: Z is a ring; slot f % ring may be overwritten once frame f - ring has been read by every row group,
+// and a finished group is counted in col_done[f].
+template <int N1, int IN, bool STAGED, bool FUSED>
+__device__ __forceinline__ void fourstep_cols_cta(const FourStepParams &a, const CUtensorMap *tmap_in, int bid, int nblk,
+                                                  unsigned char *smem_raw, unsigned long long *s_mbar) {
     using G = GeomFS<N1>;
     using F = FourStepA<N1, IN>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_mbar[2];
     const int col = threadIdx.x % G::CPC, t = threadIdx.x / G::CPC;
-    const int group = blockIdx.x % G::GROUPS_A, lane = blockIdx.x / G::GROUPS_A, lanes = gridDim.x / G::GROUPS_A;
+    const int group = bid % G::GROUPS_A, lane = bid / G::GROUPS_A, lanes = nblk / G::GROUPS_A;
     const int n2 = group * G::CPC + col;
     cf *xcol = reinterpret_cast<cf *>(smem_raw) + (size_t)col * G::CSTRIDE;
     constexpr int BPS = in_elem_bytes<IN>();
@@ -195,7 +223,7 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
     uint32_t raw[16];
     // programmatic dependent launch: the next kernel of the chain may start its (constant-table) prologue while
     // this grid drains; everything that touches Z, the IQ bytes, rows or peaks sits behind grid_dependency_wait()
-    launch_dependents();
+    if (!FUSED) launch_dependents();
     F::load_window(a.p.win, n2, t, wreg);
     F::load_pass_tw(a.tw_n1, t, twreg);
     F::load_col_tw(a.tw_n, n2, t, twz);
@@ -206,14 +234,14 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
         }
         __syncthreads();
     }
-    grid_dependency_wait();
+    if (!FUSED) grid_dependency_wait();
     const char *src0 = (const char *)a.p.in + ((size_t)t * 256 + n2) * BPS;
     if constexpr (STAGED) {
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int b = 0; b < 2; b++)
                 if (lane + b * lanes < a.nbatch)
-                    tma_load_2d(tiles + b * TILE_BYTES, &tmap_in, group * G::CPC * BPS, (int)((a.frame0 + lane + b * lanes) * N1),
+                    tma_load_2d(tiles + b * TILE_BYTES, tmap_in, group * G::CPC * BPS, (int)((a.frame0 + lane + b * lanes) * N1),
                                 TILE_BYTES, &s_mbar[b]);
         }
     } else {
@@ -221,6 +249,7 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
     }
     int it = 0;
     for (int fb = lane; fb < a.nbatch; fb += lanes, it++) {
+        if (FUSED && threadIdx.x == 0 && fb >= a.ring) wait_count(a.row_done + (fb - a.ring), G::GROUPS_B);  // slot is free
         if constexpr (STAGED) {
             const int b = it & 1;
             mbar_wait(&s_mbar[b], (uint32_t)((it >> 1) & 1));
@@ -228,7 +257,7 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
             F::first(raw, wreg, u);
             __syncthreads();  // the previous frame's second pass has read the exchange buffer; tile b is consumed
             if (threadIdx.x == 0 && fb + 2 * lanes < a.nbatch)
-                tma_load_2d(tiles + b * TILE_BYTES, &tmap_in, group * G::CPC * BPS, (int)((a.frame0 + fb + 2 * lanes) * N1), TILE_BYTES,
+                tma_load_2d(tiles + b * TILE_BYTES, tmap_in, group * G::CPC * BPS, (int)((a.frame0 + fb + 2 * lanes) * N1), TILE_BYTES,
                             &s_mbar[b]);
         } else {
             F::first(raw, wreg, u);
@@ -236,9 +265,20 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
             __syncthreads();  // the previous frame's second pass has read the exchange buffer
         }
         F::scatter(xcol, t, u);
-        __syncthreads();
-        F::second(xcol, twreg, twz, t, u, a.z + (size_t)fb * G::N + n2);
+        __syncthreads();  // (FUSED: thread 0 passed its wait_count before the first barrier of this iteration)
+        F::second(xcol, twreg, twz, t, u, a.z + (size_t)(FUSED ? fb % a.ring : fb) * G::N + n2);
+        if (FUSED) {
+            __syncthreads();
+            if (threadIdx.x == 0) publish_count(a.col_done + fb);
+        }
     }
+}
+
+template <int N1, int IN, bool STAGED>
+__global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(const FourStepParams a, const __grid_constant__ CUtensorMap tmap_in) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    fourstep_cols_cta<N1, IN, STAGED, false>(a, &tmap_in, (int)blockIdx.x, (int)gridDim.x, smem_raw, s_mbar);
 }
 
 // grid = GROUPS_B * lanes; CTA (group, lane) transforms rows 16*group .. 16*group+15 of its frames.
@@ -247,34 +287,40 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
 // has two identities: in the first pass lanes are consecutive POINTS of a row (the dense tile is read 128 bytes at
 // a time), in the second pass lanes are consecutive ROWS (= consecutive bins k1: coalesced row stores); the
 // exchange buffer between the passes is where the identity changes.
-template <int N1>
-__global__ void __launch_bounds__(256) fourstep_rows_kernel(const FourStepParams a) {
+template <int N1, bool FUSED>
+__device__ __forceinline__ void fourstep_rows_cta(const FourStepParams &a, int bid, int nblk, unsigned char *smem_raw,
+                                                  unsigned long long *s_mbar) {
     using G = GeomFS<N1>;
     using F = FourStepB<N1>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_mbar[2];
     const int row1 = threadIdx.x / 16, t1 = threadIdx.x % 16;  // first pass
     const int row = threadIdx.x % 16, t = threadIdx.x / 16;    // second pass
-    const int group = blockIdx.x % G::GROUPS_B, lane = blockIdx.x / G::GROUPS_B, lanes = gridDim.x / G::GROUPS_B;
+    const int group = bid % G::GROUPS_B, lane = bid / G::GROUPS_B, lanes = nblk / G::GROUPS_B;
     const int k1 = group * 16 + row;
     constexpr int TILE = 16 * 256;                          // points per tile
     cf *tile = reinterpret_cast<cf *>(smem_raw);           // [2][TILE] staged rows of Z, dense
     cf *xs = tile + 2 * TILE;                               // [16][RSTRIDE] exchange
     cf twreg[15];
-    launch_dependents();
+    if (!FUSED) launch_dependents();
     F::load_pass_tw(a.tw_256, t, twreg);
     if (threadIdx.x == 0) {
         mbar_init(&s_mbar[0]);
         mbar_init(&s_mbar[1]);
     }
     __syncthreads();
-    grid_dependency_wait();
+    if (!FUSED) grid_dependency_wait();
     const cf *zg = a.z + (size_t)group * TILE;
+    // FUSED: frame f sits in ring slot f % ring once all GROUPS_A column groups have counted themselves
+    auto fetch = [&](int f, int b) {
+        if (FUSED) {
+            wait_count(a.col_done + f, G::GROUPS_A);
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of other CTAs -> this TMA read
+        }
+        tma_load_1d(tile + b * TILE, zg + (size_t)(FUSED ? f % a.ring : f) * G::N, TILE * sizeof(cf), &s_mbar[b]);
+    };
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < 2; b++)
-            if (lane + b * lanes < a.nbatch)
-                tma_load_1d(tile + b * TILE, zg + (size_t)(lane + b * lanes) * G::N, TILE * sizeof(cf), &s_mbar[b]);
+            if (lane + b * lanes < a.nbatch) fetch(lane + b * lanes, b);
     }
     float pk[16];
 #pragma unroll
@@ -289,8 +335,13 @@ __global__ void __launch_bounds__(256) fourstep_rows_kernel(const FourStepParams
         cf u[16];
         F::first(tile + b * TILE + row1 * 256, t1, u);
         __syncthreads();  // the previous frame's second pass is done with xs; everybody has read tile b
-        if (threadIdx.x == 0 && fb + 2 * lanes < a.nbatch)
-            tma_load_1d(tile + b * TILE, zg + (size_t)(fb + 2 * lanes) * G::N, TILE * sizeof(cf), &s_mbar[b]);
+        if (threadIdx.x == 0) {
+            if (FUSED) {  // this row group no longer needs the frame's ring slot
+                __threadfence();
+                atomicAdd(a.row_done + fb, 1u);
+            }
+            if (fb + 2 * lanes < a.nbatch) fetch(fb + 2 * lanes, b);
+        }
         F::scatter(xs + row1 * G::RSTRIDE, t1, u);
         __syncthreads();
         float *out = a.p.rows + frame_row(a.p, f) * a.p.row_stride;
@@ -309,6 +360,27 @@ __global__ void __launch_bounds__(256) fourstep_rows_kernel(const FourStepParams
 #pragma unroll
         for (int c = 0; c < 16; c++) atomic_max_float(a.p.peaks + F::bin_of(t, k1, c), pk[c]);
     }
+}
+
+template <int N1>
+__global__ void __launch_bounds__(256) fourstep_rows_kernel(const FourStepParams a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    fourstep_rows_cta<N1, false>(a, (int)blockIdx.x, (int)gridDim.x, smem_raw, s_mbar);
+}
+
+// Both steps in ONE cooperative launch (all CTAs co-resident): CTAs 0 .. n_prod-1 produce column transforms into
+// a ring of Z frames that fits the L2, the others consume them as row transforms, frame by frame, handing over
+// through per-frame counters.  Z never travels to HBM, the two steps overlap on every SM (one is store-, the
+// other load-heavy), and there is one prologue and one tail per call instead of one per batch and step.
+template <int N1, int IN>
+__global__ void __launch_bounds__(256, 2) fourstep_fused_kernel(const FourStepParams a, const __grid_constant__ CUtensorMap tmap_in) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    if ((int)blockIdx.x < a.n_prod)
+        fourstep_cols_cta<N1, IN, true, true>(a, &tmap_in, (int)blockIdx.x, a.n_prod, smem_raw, s_mbar);
+    else
+        fourstep_rows_cta<N1, true>(a, (int)blockIdx.x - a.n_prod, (int)gridDim.x - a.n_prod, smem_raw, s_mbar);
 }
 #endif  // __CUDACC__
 

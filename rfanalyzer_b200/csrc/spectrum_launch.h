@@ -34,9 +34,10 @@ struct FourStepLaunch {
     const cf *tw_n;     // make_twiddles(N)
     cf *z;              // batch buffer
     long long z_bytes;
+    unsigned int *sync;  // 2 * nframes counters for the fused launch (NULL: two kernels per batch)
 };
 bool fourstep_supported(int N, int in_fmt, int out_kind);
-int fourstep_launches(int N, long long nframes, long long z_bytes);
+int fourstep_launches(int N, long long nframes, long long z_bytes);  // of the most recent fourstep_launch on this thread
 cudaError_t fourstep_launch(const SpectrumLaunch &L, const FourStepLaunch &fs);
 
 // small helper kernels (spectrum.cu)

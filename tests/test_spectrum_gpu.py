@@ -420,3 +420,15 @@ def test_fourstep_tensor_map_staging_equals_per_thread_loads(gpu_ctx, oracle, mo
         plan.process(buf[4:], frames, rows=rows_m)
         gpu_ctx.sync()
     assert np.array_equal(rows_m.cpu().numpy(), rows_t)
+
+
+@pytest.mark.parametrize("fmt,n,frames", [(0, 65536, 40), (2, 32768, 150)])
+def test_fourstep_fused_producer_consumer_launch(gpu_ctx, oracle, monkeypatch, fmt, n, frames):
+    """RFA_FS_FUSED=1: both steps in one cooperative launch, Z in a ring that is smaller than the call (the ring
+    hand-over is exercised: RFA_FS_RING_KIB=1024 keeps only the minimum number of frames).  Identical rows."""
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows_2k, peaks_2k, avg_2k = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
+    monkeypatch.setenv("RFA_FS_FUSED", "1")
+    monkeypatch.setenv("RFA_FS_RING_KIB", "1024")
+    rows_f, peaks_f, avg_f = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
+    assert np.array_equal(rows_f, rows_2k) and np.array_equal(peaks_f, peaks_2k) and np.array_equal(avg_f, avg_2k)
