@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "device_once.h"
 #include "kernels.h"
 #include "rfa_fft_core.cuh"
 
@@ -513,11 +514,13 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
             const int span_used = (int)((B * M + amax + 1) * D + 8);
             ta.a.span_max = span_used;
             const size_t tsmem = ((size_t)span_used + 8) * sizeof(float2) + (size_t)I * D * ta.AP * sizeof(float);
-            static bool tconfigured = false;
+            static DeviceOnce tonce;
+            int tdev = 0;
+            const bool tfirst = tonce.pending(&tdev);
             const int mx = (int)(((size_t)kSpanT + 8) * sizeof(float2) + 8192 * sizeof(float));
 #define RFA_RT(KIND, AM)                                                                                           \
     do {                                                                                                           \
-        if (!tconfigured)                                                                                          \
+        if (tfirst)                                                                                                 \
             cudaFuncSetAttribute(resample_tiled_kernel<KIND, M, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); \
         if (launch_now) resample_tiled_kernel<KIND, M, AM><<<tgrid, (unsigned)threads, tsmem, st>>>(ta);            \
     } while (0)
@@ -528,13 +531,13 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
         RFA_RT(2, AM);                               \
         RFA_RT(3, AM);                               \
     } while (0)
-            if (!tconfigured) {  // opt every instantiation in to the large shared-memory carve-out once
+            if (tfirst) {  // opt every instantiation in to the large shared-memory carve-out once per device
                 const bool launch_now = false;
                 RFA_RT_ALL(3);
                 RFA_RT_ALL(5);
                 RFA_RT_ALL(9);
                 RFA_RT_ALL(12);
-                tconfigured = true;
+                tonce.done(tdev);
             }
             {
                 const bool launch_now = true;
@@ -569,11 +572,13 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
         const size_t bank_floats = (size_t)I * nt;
         fa.bank_smem = bank_floats * sizeof(float) <= 4 * 1024 ? (int)bank_floats : 0;
         const size_t fsmem = ((size_t)kSpanMax + 8) * sizeof(float2) + (size_t)fa.bank_smem * sizeof(float);
-        static bool fconfigured = false;
+        static DeviceOnce fonce;
+        int fdev = 0;
+        const bool ffirst = fonce.pending(&fdev);
         const int mx = (int)(((size_t)kSpanMax + 8) * sizeof(float2) + 4 * 1024);
 #define RFA_RF1(KIND, BS, GG)                                                                                          \
     do {                                                                                                               \
-        if (!fconfigured)                                                                                              \
+        if (ffirst)                                                                                                    \
             cudaFuncSetAttribute(resample_fast_kernel<KIND, BS, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); \
         if (launch_now && in.kind == KIND && (fa.bank_smem != 0) == BS && G == GG)                                     \
             resample_fast_kernel<KIND, BS, GG><<<grid, 256, fsmem, st>>>(fa);                                          \
@@ -586,13 +591,13 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
         RFA_RF1(KIND, false, 16);    \
     } while (0)
         if (in.kind < 0 || in.kind > 3) return cudaErrorInvalidValue;
-        for (int pass = fconfigured ? 1 : 0; pass < 2; pass++) {
+        for (int pass = ffirst ? 0 : 1; pass < 2; pass++) {
             const bool launch_now = pass == 1;
             RFA_RF(0);
             RFA_RF(1);
             RFA_RF(2);
             RFA_RF(3);
-            fconfigured = true;
+            if (pass == 0) fonce.done(fdev);
         }
 #undef RFA_RF1
 #undef RFA_RF
@@ -605,8 +610,9 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
         else                                                                                      \
             resample_kernel<KIND, false><<<grid, 256, smem, st>>>(a);                             \
     } while (0)
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce ronce;
+    int rdev = 0;
+    if (ronce.pending(&rdev)) {
         cudaFuncSetAttribute(resample_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(resample_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(resample_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -615,7 +621,7 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
         cudaFuncSetAttribute(resample_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(resample_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(resample_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        ronce.done(rdev);
     }
     switch (in.kind) {
         case 0: RFA_RS(0); break;
@@ -651,14 +657,15 @@ cudaError_t fir_launch(const StreamDesc &in, const float *taps_re, const float *
     a.out_im = out_im;
     const unsigned grid = (unsigned)((nout + tile - 1) / tile);
     const size_t smem = (2 * (size_t)kSpanMax + 2 * (size_t)ntaps) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce konce;
+    int kdev = 0;
+    if (konce.pending(&kdev)) {
         const int mx = (int)((2 * (size_t)kSpanMax + 2 * 4096) * sizeof(float));
         cudaFuncSetAttribute(fir_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(fir_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(fir_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(fir_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        configured = true;
+        konce.done(kdev);
     }
     if (taps_im) {
         if (exact)

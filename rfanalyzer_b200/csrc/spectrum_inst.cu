@@ -1,5 +1,6 @@
 // spectrum_inst.cu -- instantiations of the fused spectrum kernel, compiled once per
 // size group (-DRFA_GROUP=0..3) so the groups build in parallel.
+#include "device_once.h"
 #include <stdlib.h>
 
 #include "spectrum_launch.h"
@@ -15,14 +16,15 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     constexpr size_t SMEM = STAGED ? staged_offset<NL, S, IN, OUT>() + staged_bytes<NL, IN>()
                                    : SpectrumFrame<NL, S, IN, OUT>::SMEM_BYTES;
     auto kern = spectrum_kernel<NL, S, IN, OUT, STAGED>;
-    static bool configured = false;
+    static DeviceOnce once;  // per instantiation
+    int dev = 0;
     cudaError_t err;
-    if (!configured) {
+    if (once.pending(&dev)) {
         if (SMEM > 48 * 1024) {
             err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
             if (err != cudaSuccess) return err;
         }
-        configured = true;
+        once.done(dev);
     }
     int occ = 0;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::CTA, SMEM);
@@ -65,12 +67,13 @@ cudaError_t launch_two(const SpectrumLaunch &L, bool query, int *grid_out, int *
     using G = Geom2<NL>;
     constexpr size_t SMEM = SpectrumFrame2<NL, IN>::SMEM_BYTES;
     auto kern = spectrum2_kernel<NL, IN>;
-    static bool configured = false;
+    static DeviceOnce once;
+    int dev = 0;
     cudaError_t err;
-    if (!configured) {
+    if (once.pending(&dev)) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (err != cudaSuccess) return err;
-        configured = true;
+        once.done(dev);
     }
     int occ = 0;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::CTA, SMEM);
@@ -98,11 +101,12 @@ template <int IN>
 cudaError_t launch_64(const SpectrumLaunch &L) {
     using G = Geom64;
     auto kern = spectrum64_kernel<IN>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    int dev = 0;
+    if (once.pending(&dev)) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
         if (err != cudaSuccess) return err;
-        configured = true;
+        once.done(dev);
     }
     long long need = (L.p.nframes + G::SLOTS - 1) / G::SLOTS;
     long long grid = need < L.num_sms ? need : L.num_sms;
