@@ -358,8 +358,9 @@ def main():
                          "frac": achieved / peak_gbs, "traffic": ncu_traffic(),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_us_per_launch": kernel_ms * 1e3,
                          "peak_source": peak_src,
-                         "note": "at 6 B/sample the 4096-pt FFT is bound by the FP32 pipe (48% busy) and the shared-memory "
-                                 "pipe (51% busy) together, not by HBM: DESIGN.md 4.1, profiles/r01b_*"},
+                         "note": "at 6 B/sample the 4096-pt FFT is not HBM-bound on CUDA cores: issue slots cap it at ~0.55 of this "
+                                 "roofline (packed FP32 instructions hold the scheduler two cycles), FP32 pipe 48% and shared-"
+                                 "memory pipe 51% busy: DESIGN.md 4.1, profiles/r01b_*"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
