@@ -2,6 +2,7 @@
 // size group (-DRFA_GROUP=0..3) so the groups build in parallel.
 #include "device_once.h"
 #include "spectrum_pair_kernel.cuh"
+#include "spectrum_lean_kernel.cuh"
 #include <stdlib.h>
 
 #include "spectrum_launch.h"
@@ -143,6 +144,43 @@ cudaError_t launch_pair(const SpectrumLaunch &L, bool query, int *grid_out, int 
     kern<<<(unsigned)grid, G::CTA, SMEM, L.stream>>>(L.p);
     return cudaGetLastError();
 }
+// three-CTAs-per-SM kernel for N = 4096, 8-bit IQ (spectrum_lean_kernel.cuh)
+template <int IN>
+cudaError_t launch_lean(const SpectrumLaunch &L, bool query, int *grid_out, int *spc_out) {
+    using G = GeomLean;
+    constexpr size_t SMEM = G::smem(in_elem_bytes<IN>());
+    auto kern = spectrum_lean_kernel<IN>;
+    static DeviceOnce once;
+    int dev = 0;
+    if (once.pending(&dev)) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (err != cudaSuccess) return err;
+        once.done(dev);
+    }
+    int occ = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::CTA, SMEM);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
+    const long long need = L.p.nframes;
+    if (need > 0x7FFF0000LL) return cudaErrorInvalidValue;  // chunk indices are 32-bit in the kernel
+    const bool avg_cta = L.p.avg != nullptr;  // the averaging CTA takes one resident slot
+    long long cap = (long long)L.num_sms * occ;
+    if (L.max_grid > 0 && L.max_grid < cap) cap = L.max_grid;
+    if (avg_cta && cap > 1) cap -= 1;
+    long long grid = need < cap ? need : cap;
+    if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
+    if (spc_out) *spc_out = 1;
+    if (query) return cudaSuccess;
+    if (avg_cta) grid += 1;
+    kern<<<(unsigned)grid, G::CTA, SMEM, L.stream>>>(L.p);
+    return cudaGetLastError();
+}
+static bool lean_enabled(const void *iq) {
+    const char *e = getenv("RFA_LEAN");  // read at every launch so that tests and timing runs can switch
+    return e && atoi(e) == 1 && ((size_t)iq & 15) == 0;
+}
+
 static bool pair_enabled(const void *iq) {
     const char *e = getenv("RFA_PAIR");  // read at every launch so that tests and timing runs can switch
     return e && atoi(e) == 1 && ((size_t)iq & 15) == 0;
@@ -169,6 +207,14 @@ cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc
                 case FMT_S8: return launch_64<FMT_S8>(L);
                 case FMT_U8: return launch_64<FMT_U8>(L);
                 case FMT_S16LE: return launch_64<FMT_S16LE>(L);
+            }
+        }
+    }
+    if constexpr (S == 1 && NL == 4096) {
+        if (L.out_kind == OUT_DB && lean_enabled(L.p.in)) {
+            switch (L.in_fmt) {
+                case FMT_S8: return launch_lean<FMT_S8>(L, query, grid, spc);
+                case FMT_U8: return launch_lean<FMT_U8>(L, query, grid, spc);
             }
         }
     }

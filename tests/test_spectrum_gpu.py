@@ -487,3 +487,55 @@ def test_pair_kernel_ring_history_and_repeated_launches(gpu_ctx, oracle, monkeyp
             L_o.orc_time_average(proc, L, avg_ref)
             assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
     L_o.orc_fftproc_free(proc)
+
+
+# ---- three-CTAs-per-SM kernel (spectrum_lean_kernel.cuh, RFA_LEAN=1), N = 4096, 8-bit IQ ----
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("frames", [1, 2, 37, 600, 4096])
+def test_lean_kernel_is_identical_to_the_default_kernel(gpu_ctx, oracle, monkeypatch, fmt, frames):
+    """Window taps from shared memory and last-pass twiddles through L1 instead of registers, one exchange frame,
+    three CTAs per SM: the same operations in the same order, so rows, peaks and average are bit-identical."""
+    n = 4096
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows_d, peaks_d, avg_d = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
+    monkeypatch.setenv("RFA_LEAN", "1")
+    rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
+    assert np.array_equal(rows, rows_d) and np.array_equal(peaks, peaks_d) and np.array_equal(avg, avg_d)
+    if frames <= 64:
+        r, p, a = oracle.spectrum_run(fmt, iq, n, 8)
+        assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL and np.abs(avg - a).max() < DB_TOL
+
+
+def test_lean_kernel_ring_history_and_repeated_launches(gpu_ctx, oracle, monkeypatch):
+    import torch
+    import rfanalyzer_b200 as rfa
+    monkeypatch.setenv("RFA_LEAN", "1")
+    n, L, ring = 4096, 5, 300
+    L_o = oracle.lib()
+    proc = L_o.orc_fftproc_new(ring, 1)
+    plan = rfa.SpectrumPlan(gpu_ctx, 1, n, avg_len=L)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
+        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
+        write_index, history, first = 0, 0, 0
+        for call, frames in enumerate((3, 1, 311, 8, 2, 2, 2, 75)):
+            iq = oracle.synth_iq(1, n * frames, first=first)
+            first += n * frames
+            r, _, _ = oracle.spectrum_run(1, iq, n, 0)
+            for k in range(frames):
+                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
+            plan.process(torch.from_numpy(iq).cuda(), frames, rows=d_ring, peaks=d_peaks, avg=d_avg,
+                         row0=write_index, row_step=-1, ring_rows=ring, history_rows=history,
+                         peaks_accumulate=call > 0)
+            gpu_ctx.sync()
+            write_index = (write_index - frames) % ring
+            history = min(ring, history + frames)
+            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
+            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
+            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
+            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
+            avg_ref = np.empty(n, np.float32)
+            L_o.orc_time_average(proc, L, avg_ref)
+            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
+    L_o.orc_fftproc_free(proc)
