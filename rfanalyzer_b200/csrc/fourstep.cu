@@ -115,6 +115,22 @@ cudaError_t run_fused(const SpectrumLaunch &L, const FourStepLaunch &fs, const C
     return e;
 }
 
+// the batch buffer Z as a [frames * N1][512] float matrix, box = the N1 x CPC points one column group finishes per frame
+template <int N1>
+bool make_z_map(cf *z, long long batch_frames, CUtensorMap *tm) {
+    using G = GeomFS<N1>;
+    const char *e = getenv("RFA_FS_ZTMA");  // RFA_FS_ZTMA=0: per-thread stores of Z (A/B timing runs)
+    if (e && atoi(e) == 0) return false;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || ((size_t)z & 15) != 0 || batch_frames * N1 > 0xFFFFFFFFLL) return false;
+    const cuuint64_t dims[2] = {512, (cuuint64_t)batch_frames * N1};
+    const cuuint64_t strides[1] = {512 * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)(G::CPC * 2), (cuuint32_t)N1};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, z, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int N1, int IN>
 cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     using G = GeomFS<N1>;
@@ -144,6 +160,19 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     const int occ_a = occ_as[staged];
     const long long batch = fs.z_bytes / ((long long)G::N * (long long)sizeof(cf));
     if (batch < 1) return cudaErrorInvalidValue;
+    alignas(64) CUtensorMap tmap_z;
+    memset(&tmap_z, 0, sizeof(tmap_z));
+    // measured (gpurun_out/fs_timing6.log): 2.5 % faster for 8-bit IQ, 8 % slower for int16 IQ, whose raw tiles are
+    // twice as large (the store tile then costs the second resident CTA its shared memory head-room)
+    const bool ztma = staged && BPS == 2 && make_z_map<N1>(fs.z, batch, &tmap_z);
+    auto kz = fourstep_cols_ztma_kernel<N1, IN>;
+    const size_t smem_z = G::smem_a_zstore(BPS);
+    static thread_local int dev_done_z = -1, occ_z = 1;
+    if (ztma && dev_done_z != dev) {
+        e = resident_ctas(kz, smem_z, &occ_z);
+        if (e != cudaSuccess) return e;
+        dev_done_z = dev;
+    }
     const char *ep = getenv("RFA_FS_PDL");  // RFA_FS_PDL=0: plain stream order (A/B timing runs)
     const bool pdl = !(ep && atoi(ep) == 0);
     FourStepParams a{};
@@ -157,7 +186,7 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
         const long long nb = L.p.nframes - f0 < batch ? L.p.nframes - f0 : batch;
         a.frame0 = f0;
         a.nbatch = (int)nb;
-        long long lanes_a = (long long)L.num_sms * occ_a / G::GROUPS_A, lanes_b = (long long)L.num_sms * occ_b / G::GROUPS_B;
+        long long lanes_a = (long long)L.num_sms * (ztma ? occ_z : occ_a) / G::GROUPS_A, lanes_b = (long long)L.num_sms * occ_b / G::GROUPS_B;
         if (lanes_a < 1) lanes_a = 1;
         if (lanes_b < 1) lanes_b = 1;
         if (lanes_a > nb) lanes_a = nb;
@@ -173,8 +202,8 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cfg.gridDim = dim3((unsigned)(lanes_a * G::GROUPS_A));
-        cfg.dynamicSmemBytes = smem_a;
-        e = cudaLaunchKernelEx(&cfg, ka, a, tmap);
+        cfg.dynamicSmemBytes = ztma ? smem_z : smem_a;
+        e = ztma ? cudaLaunchKernelEx(&cfg, kz, a, tmap, tmap_z) : cudaLaunchKernelEx(&cfg, ka, a, tmap);
         if (e != cudaSuccess) return e;
         cfg.gridDim = dim3((unsigned)(lanes_b * G::GROUPS_B));
         cfg.dynamicSmemBytes = G::SMEM_B;

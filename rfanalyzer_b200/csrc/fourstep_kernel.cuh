@@ -54,6 +54,9 @@ struct GeomFS {
     static constexpr size_t XCHG_A = (SMEM_A + 127) / 128 * 128;
     static RFA_CX size_t tile_bytes(int bps) { return (size_t)N1 * CPC * bps; }
     static RFA_CX size_t smem_a_staged(int bps) { return XCHG_A + 2 * tile_bytes(bps); }
+    // ... and, when Z leaves through a tensor-map store, one tile [N1][CPC] of finished Z points behind them
+    static constexpr size_t ZTILE_BYTES = (size_t)N1 * CPC * sizeof(cf);
+    static RFA_CX size_t smem_a_zstore(int bps) { return smem_a_staged(bps) + ZTILE_BYTES; }
     static constexpr size_t SMEM_B = (size_t)(2 * 16 * 256 + 16 * RSTRIDE) * sizeof(cf);  // two dense Z tiles + exchange
     static RFA_CX size_t smem_fused(int bps) { return smem_a_staged(bps) > SMEM_B ? smem_a_staged(bps) : SMEM_B; }
     static_assert(N1 == 128 || N1 == 256, "four-step covers N = 32768 and 65536");
@@ -103,7 +106,8 @@ struct FourStepA {
     }
     static RFA_HD void scatter(cf *xcol, int t, const cf *u) { pass_scatter<N1, T1, 16, 1>(xcol, t, u); }
     // second pass + column twiddle; z points at Z[frame][0][n2]
-    static RFA_HD void second(const cf *xcol, const cf *twreg, const cf *twz, int t, cf *u, cf *z) {
+    // (`zstride` = points between consecutive k1: 256 in Z itself, CPC in the column kernel's staged store tile)
+    static RFA_HD void second(const cf *xcol, const cf *twreg, const cf *twz, int t, cf *u, cf *z, int zstride = 256) {
         constexpr int STR = N1 / R1;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
@@ -118,7 +122,7 @@ struct FourStepA {
 #pragma unroll
             for (int c = 0; c < R1; c++) {
                 const int e = b * R1 + c;
-                z[(size_t)k1_of(t, e) * 256] = cmul(u[b * R1 + Dft<R1>::perm(c)], twz[e]);
+                z[(size_t)k1_of(t, e) * zstride] = cmul(u[b * R1 + Dft<R1>::perm(c)], twz[e]);
             }
         }
     }
@@ -183,6 +187,16 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0,
 // tensor-map box per frame in a two-deep ring (the per-thread version issues 16 two-byte loads per frame and
 // stalls on the load/store queue: ncu lg_throttle 2.0, gpurun_out/prof_fs1).  `tmap_in` views the IQ bytes of the
 // call as [frames * N1][256 * bytes-per-pair] uint8.
+// 2-D tiled bulk store (TMA): a dense shared-memory tile to box {c0 .., c1 ..} of the tensor map, as one bulk group
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, const void *src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // cross-CTA hand-over of the fused launch: a frame's counter is bumped once per finished group, after a CTA
 // barrier and a device-scope fence (the stores of all 256 threads are then visible to whoever acquires the count)
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
@@ -206,9 +220,12 @@ __device__ __forceinline__ void publish_count(unsigned int *p) {  // call by ONE
 // One CTA of step A: column group bid % GROUPS_A of frames bid / GROUPS_A, + lanes, ...
 // FUSED: Z is a ring; slot f % ring may be overwritten once frame f - ring has been read by every row group,
 // and a finished group is counted in col_done[f].
-template <int N1, int IN, bool STAGED, bool FUSED>
+// ZTMA: the finished Z points of a frame are collected in a dense tile [N1][CPC] and leave as ONE tensor-map store
+// (`tmap_z` views the batch buffer as [batch * N1][512] floats) instead of 16 eight-byte stores per thread.
+template <int N1, int IN, bool STAGED, bool FUSED, bool ZTMA = false>
 __device__ __forceinline__ void fourstep_cols_cta(const FourStepParams &a, const CUtensorMap *tmap_in, int bid, int nblk,
-                                                  unsigned char *smem_raw, unsigned long long *s_mbar) {
+                                                  unsigned char *smem_raw, unsigned long long *s_mbar,
+                                                  const CUtensorMap *tmap_z = nullptr) {
     using G = GeomFS<N1>;
     using F = FourStepA<N1, IN>;
     const int col = threadIdx.x % G::CPC, t = threadIdx.x / G::CPC;
@@ -265,13 +282,23 @@ __device__ __forceinline__ void fourstep_cols_cta(const FourStepParams &a, const
             __syncthreads();  // the previous frame's second pass has read the exchange buffer
         }
         F::scatter(xcol, t, u);
+        if (ZTMA && threadIdx.x == 0 && it > 0) tma_store_wait_read();  // the previous frame's store has read the tile
         __syncthreads();  // (FUSED: thread 0 passed its wait_count before the first barrier of this iteration)
-        F::second(xcol, twreg, twz, t, u, a.z + (size_t)(FUSED ? fb % a.ring : fb) * G::N + n2);
+        if constexpr (ZTMA) {
+            cf *ztile = reinterpret_cast<cf *>(smem_raw + G::smem_a_staged(BPS));
+            F::second(xcol, twreg, twz, t, u, ztile + col, G::CPC);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // these stores, then the bulk store's reads
+            __syncthreads();
+            if (threadIdx.x == 0) tma_store_2d(tmap_z, group * G::CPC * 2, fb * N1, ztile);
+        } else {
+            F::second(xcol, twreg, twz, t, u, a.z + (size_t)(FUSED ? fb % a.ring : fb) * G::N + n2);
+        }
         if (FUSED) {
             __syncthreads();
             if (threadIdx.x == 0) publish_count(a.col_done + fb);
         }
     }
+    if (ZTMA && threadIdx.x == 0) tma_store_wait_all();  // the last tile is in Z before the CTA leaves
 }
 
 template <int N1, int IN, bool STAGED>
@@ -279,6 +306,15 @@ __global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_kernel(cons
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_mbar[2];
     fourstep_cols_cta<N1, IN, STAGED, false>(a, &tmap_in, (int)blockIdx.x, (int)gridDim.x, smem_raw, s_mbar);
+}
+
+// tensor-map loads AND store
+template <int N1, int IN>
+__global__ void __launch_bounds__(256, RFA_FS_MINCTAS) fourstep_cols_ztma_kernel(const FourStepParams a, const __grid_constant__ CUtensorMap tmap_in,
+                                                                                const __grid_constant__ CUtensorMap tmap_z) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    fourstep_cols_cta<N1, IN, true, false, true>(a, &tmap_in, (int)blockIdx.x, (int)gridDim.x, smem_raw, s_mbar, &tmap_z);
 }
 
 // grid = GROUPS_B * lanes; CTA (group, lane) transforms rows 16*group .. 16*group+15 of its frames.

@@ -411,6 +411,10 @@ def test_fourstep_tensor_map_staging_equals_per_thread_loads(gpu_ctx, oracle, mo
     rows_l, peaks_l, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
     monkeypatch.delenv("RFA_FS_TMA")
     assert np.array_equal(rows_t, rows_l) and np.array_equal(peaks_t, peaks_l)
+    monkeypatch.setenv("RFA_FS_ZTMA", "0")   # tensor-map loads, per-thread stores of the intermediate
+    rows_s, peaks_s, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
+    monkeypatch.delenv("RFA_FS_ZTMA")
+    assert np.array_equal(rows_t, rows_s) and np.array_equal(peaks_t, peaks_s)
     # an input that starts 4 bytes into an allocation is not 16-byte aligned: the launcher must fall back by itself
     plan = rfa.SpectrumPlan(gpu_ctx, fmt, n)
     with torch.cuda.stream(gpu_ctx.torch_stream):
