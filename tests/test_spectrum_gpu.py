@@ -543,3 +543,33 @@ def test_lean_kernel_ring_history_and_repeated_launches(gpu_ctx, oracle, monkeyp
             L_o.orc_time_average(proc, L, avg_ref)
             assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
     L_o.orc_fftproc_free(proc)
+
+
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_fourstep_no_rows_peak_only_and_host_buffers(gpu_ctx, oracle, n):
+    """The four-step path behind every output mode of rfa_spectrum_process: no rows (only the newest L+1 rows are
+    kept for the average), peaks only, average only, and host buffers (chunked H2D -> kernels -> D2H pipeline)."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    frames, L = 11, 3
+    iq = oracle.synth_iq(0, n * frames)
+    r, p, a = oracle.spectrum_run(0, iq, n, L)
+    plan = rfa.SpectrumPlan(gpu_ctx, 0, n, avg_len=L)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d = torch.from_numpy(iq).cuda()
+        peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        avg = torch.zeros(n, dtype=torch.float32, device="cuda")
+        plan.process(d, frames, rows=None, peaks=peaks, avg=avg)
+        gpu_ctx.sync()
+        assert np.abs(peaks.cpu().numpy() - p).max() < DB_TOL and np.abs(avg.cpu().numpy() - a).max() < DB_TOL
+        peaks.zero_()
+        plan.process(d, frames, rows=None, peaks=peaks)
+        gpu_ctx.sync()
+        assert np.abs(peaks.cpu().numpy() - p).max() < DB_TOL
+        avg.zero_()
+        plan.process(d, frames, rows=None, avg=avg)
+        gpu_ctx.sync()
+        assert np.abs(avg.cpu().numpy() - a).max() < DB_TOL
+    h_rows, h_peaks, h_avg = np.zeros((frames, n), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    plan.process(iq, frames, rows=h_rows, peaks=h_peaks, avg=h_avg)
+    assert np.abs(h_rows - r).max() < DB_TOL and np.abs(h_peaks - p).max() < DB_TOL and np.abs(h_avg - a).max() < DB_TOL
