@@ -169,10 +169,6 @@ struct FourStepB {
 #ifndef RFA_FS_MINCTAS
 #define RFA_FS_MINCTAS 2  // two resident column CTAs per SM (128 registers; 144 without the cap)
 #endif
-// PTX griddepcontrol (sm_90+): no-ops when the kernel was launched without the programmatic-serialization attribute
-__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // 2-D tiled bulk copy (TMA): box {c0 .. , c1 ..} of the tensor map into shared memory, completion on an mbarrier
 __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint32_t bytes, unsigned long long *mbar) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

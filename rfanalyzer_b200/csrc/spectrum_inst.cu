@@ -52,6 +52,25 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     if (spc_out) *spc_out = G::FPC;
     if (query) return cudaSuccess;
     if (avg_cta) grid += 1;
+    if constexpr (STAGED) {
+        // back-to-back launches overlap: programmatic stream serialization + griddepcontrol in the kernel (RFA_PDL=0: off)
+        const char *e = getenv("RFA_PDL");
+        if (!(e && atoi(e) == 0)) {
+            SpectrumParams pp = L.p;
+            pp.pdl = 1;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(G::CTA);
+            cfg.dynamicSmemBytes = SMEM;
+            cfg.stream = L.stream;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, kern, pp);
+        }
+    }
     kern<<<(unsigned)grid, G::CTA, SMEM, L.stream>>>(L.p);
     return cudaGetLastError();
 }

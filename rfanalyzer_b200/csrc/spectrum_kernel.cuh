@@ -51,6 +51,7 @@ struct SpectrumParams {
     int avg_len;          // L
     unsigned int *ticket; // [8] zeroed counters: [c] finished tail rows, [4+c] CTAs done averaging (residue c < 4)
     float inv_n2;         // dB bias -3.0103*log2(N) (the 1/N^2 scaling, applied after the logarithm)
+    int pdl;              // launched with programmatic stream serialization (STAGED kernels): constants first, then wait
 };
 
 template <int NL>
@@ -324,6 +325,10 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
         atomicMin((unsigned int *)addr, __float_as_uint(v));
 }
 
+// PTX griddepcontrol (sm_90+): no-ops when the kernel was launched without the programmatic-serialization attribute
+__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA-staged raw IQ (STAGED kernels): the raw codes of a chunk arrive in shared memory by one bulk
 // copy (UBLKCP, completion on an mbarrier) issued by a single thread two iterations ahead, instead of
 // 16 two-byte LDGs per thread held in 16 registers for a whole iteration.
@@ -496,7 +501,13 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     const bool want_peak = (OUT == OUT_DB) && p.peaks != nullptr;
     const int n_tail = want_avg ? (int)(p.nframes < p.avg_len + 1 ? p.nframes : p.avg_len + 1) : 0;
     const int nworkers = (int)gridDim.x - (want_avg ? 1 : 0);  // the launcher adds the averaging CTA
+    // Programmatic dependent launch (p.pdl, STAGED kernels launched back to back): the next launch's CTAs take the
+    // slots this grid's CTAs free, load their constant tables while this grid drains, and only then wait for it --
+    // everything that touches IQ bytes, rows, peaks or the ticket counters sits behind grid_dependency_wait().
+    const bool pdl = STAGED && p.pdl != 0;
+    if (pdl) launch_dependents();
     if ((int)blockIdx.x == nworkers) {
+        if (pdl) grid_dependency_wait();
         average_cta(p, S, N, n_tail);
         retire_cta(p);
         return;
@@ -516,20 +527,21 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     uint32_t raw[F::PREFETCH ? E : 1];
     constexpr size_t CHUNK_BYTES = (size_t)FPC * NL * BPS;
     unsigned char *stage = smem_raw + staged_offset<NL, S, IN, OUT>();  // [2][CHUNK_BYTES] (STAGED)
-    if constexpr (STAGED) {  // the first two chunks start moving before anything else
-        if (threadIdx.x == 0) {
-            mbar_init(&s_mbar[0]);
-            mbar_init(&s_mbar[1]);
-            const int qs[2] = {q, q_next};
+    auto start_chunks = [&]() {  // thread 0: the first two chunks start moving
+        mbar_init(&s_mbar[0]);
+        mbar_init(&s_mbar[1]);
+        const int qs[2] = {q, q_next};
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
-                long long f0;
-                uint32_t bytes;
-                chunk_block<NL, FPC, BPS>(p.nframes, qs[b], &f0, &bytes);
-                if (qs[b] < nchunks && bytes)
-                    tma_load_1d(stage + b * CHUNK_BYTES, (const char *)p.in + f0 * (long long)NL * BPS, bytes, &s_mbar[b]);
-            }
+        for (int b = 0; b < 2; b++) {
+            long long f0;
+            uint32_t bytes;
+            chunk_block<NL, FPC, BPS>(p.nframes, qs[b], &f0, &bytes);
+            if (qs[b] < nchunks && bytes)
+                tma_load_1d(stage + b * CHUNK_BYTES, (const char *)p.in + f0 * (long long)NL * BPS, bytes, &s_mbar[b]);
         }
+    };
+    if constexpr (STAGED) {  // before anything else -- unless the previous launch may still be running
+        if (!pdl && threadIdx.x == 0) start_chunks();
     } else if constexpr (F::PREFETCH) {  // first: get the raw IQ of the first frame moving
         const long long v = (long long)q * FPC + sub;
         if (v < p.nframes) F::load_raw((const char *)p.in + ((p.nframes - 1 - v) * (long long)N + tid) * BPS, raw);
@@ -561,6 +573,12 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     const float inv_n2 = p.inv_n2;
     bool worked = false;
     unsigned int pending = 0;
+    if constexpr (STAGED) {
+        if (pdl) {
+            grid_dependency_wait();
+            if (threadIdx.x == 0) start_chunks();
+        }
+    }
     if (threadIdx.x == 0) pending = atomicAdd(p.ticket + TICKET_WORK + c, 1u);
     __syncthreads();  // twiddle copy
 
