@@ -52,7 +52,7 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     if (spc_out) *spc_out = G::FPC;
     if (query) return cudaSuccess;
     if (avg_cta) grid += 1;
-    if constexpr (STAGED) {
+    {
         // back-to-back launches overlap: programmatic stream serialization + griddepcontrol in the kernel (RFA_PDL=0: off)
         const char *e = getenv("RFA_PDL");
         if (!(e && atoi(e) == 0)) {

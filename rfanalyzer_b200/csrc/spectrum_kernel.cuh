@@ -51,7 +51,7 @@ struct SpectrumParams {
     int avg_len;          // L
     unsigned int *ticket; // [8] zeroed counters: [c] finished tail rows, [4+c] CTAs done averaging (residue c < 4)
     float inv_n2;         // dB bias -3.0103*log2(N) (the 1/N^2 scaling, applied after the logarithm)
-    int pdl;              // launched with programmatic stream serialization (STAGED kernels): constants first, then wait
+    int pdl;              // launched with programmatic stream serialization: constant tables first, then wait for the previous grid
 };
 
 template <int NL>
@@ -501,10 +501,10 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     const bool want_peak = (OUT == OUT_DB) && p.peaks != nullptr;
     const int n_tail = want_avg ? (int)(p.nframes < p.avg_len + 1 ? p.nframes : p.avg_len + 1) : 0;
     const int nworkers = (int)gridDim.x - (want_avg ? 1 : 0);  // the launcher adds the averaging CTA
-    // Programmatic dependent launch (p.pdl, STAGED kernels launched back to back): the next launch's CTAs take the
+    // Programmatic dependent launch (p.pdl, kernels launched back to back): the next launch's CTAs take the
     // slots this grid's CTAs free, load their constant tables while this grid drains, and only then wait for it --
     // everything that touches IQ bytes, rows, peaks or the ticket counters sits behind grid_dependency_wait().
-    const bool pdl = STAGED && p.pdl != 0;
+    const bool pdl = p.pdl != 0;
     if (pdl) launch_dependents();
     if ((int)blockIdx.x == nworkers) {
         if (pdl) grid_dependency_wait();
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
         if (!pdl && threadIdx.x == 0) start_chunks();
     } else if constexpr (F::PREFETCH) {  // first: get the raw IQ of the first frame moving
         const long long v = (long long)q * FPC + sub;
-        if (v < p.nframes) F::load_raw((const char *)p.in + ((p.nframes - 1 - v) * (long long)N + tid) * BPS, raw);
+        if (!pdl && v < p.nframes) F::load_raw((const char *)p.in + ((p.nframes - 1 - v) * (long long)N + tid) * BPS, raw);
     }
 
     // middle-pass twiddle tables: one shared-memory copy per CTA
@@ -573,10 +573,13 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     const float inv_n2 = p.inv_n2;
     bool worked = false;
     unsigned int pending = 0;
-    if constexpr (STAGED) {
-        if (pdl) {
-            grid_dependency_wait();
+    if (pdl) {
+        grid_dependency_wait();
+        if constexpr (STAGED) {
             if (threadIdx.x == 0) start_chunks();
+        } else if constexpr (F::PREFETCH) {
+            const long long v = (long long)q * FPC + sub;
+            if (v < p.nframes) F::load_raw((const char *)p.in + ((p.nframes - 1 - v) * (long long)N + tid) * BPS, raw);
         }
     }
     if (threadIdx.x == 0) pending = atomicAdd(p.ticket + TICKET_WORK + c, 1u);
