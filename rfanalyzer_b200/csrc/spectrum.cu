@@ -54,6 +54,9 @@ void reduce_peaks(const float *partial, int slots, int N, float *peaks, bool acc
 // float32 and divided by (L+1).  Rows that were never written hold -9999f (FftProcessor.kt:181).
 __global__ void average_rows_kernel(const float *rows, long long newest, long long dir, long long ring_rows,
                                     long long row_stride, long long valid, int L, int N, float *avg) {
+    // chained by programmatic dependent launch between the four-step row kernel and the next call's column kernel
+    launch_dependents();
+    grid_dependency_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float sum = 0.0f;
@@ -73,7 +76,16 @@ __global__ void average_rows_kernel(const float *rows, long long newest, long lo
 }
 void average_rows(const float *rows, long long newest, long long dir, long long ring_rows, long long row_stride,
                   long long valid, int L, int N, float *avg, cudaStream_t s) {
-    average_rows_kernel<<<(N + 127) / 128, 128, 0, s>>>(rows, newest, dir, ring_rows, row_stride, valid, L, N, avg);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((N + 127) / 128));
+    cfg.blockDim = dim3(128);
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, average_rows_kernel, rows, newest, dir, ring_rows, row_stride, valid, L, N, avg);
 }
 
 // FftProcessor.kt:150-156: sequential float32 sum of mag[b0..b1) divided by the bin count.
