@@ -573,3 +573,46 @@ def test_fourstep_no_rows_peak_only_and_host_buffers(gpu_ctx, oracle, n):
     h_rows, h_peaks, h_avg = np.zeros((frames, n), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
     plan.process(iq, frames, rows=h_rows, peaks=h_peaks, avg=h_avg)
     assert np.abs(h_rows - r).max() < DB_TOL and np.abs(h_peaks - p).max() < DB_TOL and np.abs(h_avg - a).max() < DB_TOL
+
+
+@pytest.mark.parametrize("fmt,n,ring", [(0, 256, 300), (1, 1024, 300), (0, 4096, 300), (2, 8192, 40), (0, 32768, 24)])
+def test_back_to_back_calls_without_host_synchronisation(gpu_ctx, oracle, fmt, n, ring):
+    """Consecutive launches overlap (programmatic dependent launch): a call's kernels start their prologue while the
+    previous call drains.  Many calls into the same backwards ring, accumulating peaks, an average that reads earlier
+    calls' rows -- queued WITHOUT any host synchronisation in between, checked once at the end."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    L = 6
+    L_o = oracle.lib()
+    proc = L_o.orc_fftproc_new(ring, 1)
+    plan = rfa.SpectrumPlan(gpu_ctx, fmt, n, avg_len=L)
+    counts = [3, 1, 2, 7, 1, 1, 5, 2, 9, 4, 1, 3, 2, 2, 6, 1, 8, 3, 1, 2]
+    inputs, first = [], 0
+    for frames in counts:
+        iq = oracle.synth_iq(fmt, n * frames, first=first)
+        first += n * frames
+        r, _, _ = oracle.spectrum_run(fmt, iq, n, 0)
+        for k in range(frames):
+            L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
+        inputs.append(iq)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d_in = [torch.from_numpy(iq).cuda() for iq in inputs]
+        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
+        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
+        gpu_ctx.sync()
+        write_index, history = 0, 0
+        for call, frames in enumerate(counts):      # no synchronisation inside this loop
+            plan.process(d_in[call], frames, rows=d_ring, peaks=d_peaks, avg=d_avg, row0=write_index, row_step=-1,
+                         ring_rows=ring, history_rows=history, peaks_accumulate=call > 0)
+            write_index = (write_index - frames) % ring
+            history = min(ring, history + frames)
+        gpu_ctx.sync()
+    ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
+    assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
+    peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
+    assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
+    avg_ref = np.empty(n, np.float32)
+    L_o.orc_time_average(proc, L, avg_ref)
+    assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
+    L_o.orc_fftproc_free(proc)
