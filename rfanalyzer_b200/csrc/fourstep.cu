@@ -42,7 +42,7 @@ bool make_input_map(const void *iq, long long nframes, int bps, CUtensorMap *tm)
     const char *e = getenv("RFA_FS_TMA");  // RFA_FS_TMA=0: per-thread loads (A/B timing runs, the fallback's test)
     if (e && atoi(e) == 0) return false;
     EncodeTiledFn enc = encode_tiled();
-    if (!enc || ((size_t)iq & 15) != 0 || nframes * N1 > 0xFFFFFFFFLL) return false;
+    if (!enc || ((size_t)iq & 15) != 0 || nframes * N1 > 0x7FFFFFFFLL) return false;  // box coordinates are 32-bit signed
     const cuuint64_t dims[2] = {(cuuint64_t)256 * bps, (cuuint64_t)nframes * N1};
     const cuuint64_t strides[1] = {(cuuint64_t)256 * bps};
     const cuuint32_t box[2] = {(cuuint32_t)(G::CPC * bps), (cuuint32_t)N1};
@@ -122,7 +122,7 @@ bool make_z_map(cf *z, long long batch_frames, CUtensorMap *tm) {
     const char *e = getenv("RFA_FS_ZTMA");  // RFA_FS_ZTMA=0: per-thread stores of Z (A/B timing runs)
     if (e && atoi(e) == 0) return false;
     EncodeTiledFn enc = encode_tiled();
-    if (!enc || ((size_t)z & 15) != 0 || batch_frames * N1 > 0xFFFFFFFFLL) return false;
+    if (!enc || ((size_t)z & 15) != 0 || batch_frames * N1 > 0x7FFFFFFFLL) return false;
     const cuuint64_t dims[2] = {512, (cuuint64_t)batch_frames * N1};
     const cuuint64_t strides[1] = {512 * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)(G::CPC * 2), (cuuint32_t)N1};
