@@ -268,6 +268,14 @@ cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc
             }
         }
     }
+    if constexpr (S == 1 && NL == 16384) {  // 8-bit IQ: two 32 KB chunk buffers fit beside the 139 KB exchange frame
+        if (staged_enabled(L.p.in)) {
+            switch (L.in_fmt) {
+                case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB, true>(L, query, grid, spc);
+                case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB, true>(L, query, grid, spc);
+            }
+        }
+    }
     switch (L.in_fmt) {
         case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB>(L, query, grid, spc);
         case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB>(L, query, grid, spc);

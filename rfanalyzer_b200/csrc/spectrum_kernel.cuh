@@ -163,11 +163,13 @@ struct SpectrumFrame {
     }
 
     // phase 0 (non-prefetching formats and split transforms): gather + convert + window + fold
-    static RFA_HD void first(const SpectrumParams &p, long long f, int c, int tid, const float *wreg, cf *u) {
+    static RFA_HD void first(const SpectrumParams &p, long long f, int c, int tid, const float *wreg, cf *u,
+                             const char *staged = nullptr) {
         constexpr int R = PL::radix(0);
         constexpr int NB = E / R, STR = NL / R;
         // one 64-bit address per frame; every point of this thread is a constant offset from it
-        const char *src = (const char *)p.in + (f * (long long)N + tid) * in_elem_bytes<IN>();
+        // (`staged`: the frame's raw codes in shared memory instead -- STAGED kernels with 32 points per thread)
+        const char *src = (staged ? staged : (const char *)p.in + f * (long long)N * in_elem_bytes<IN>()) + (size_t)tid * in_elem_bytes<IN>();
         const float *src_im = (IN == FMT_PF32) ? p.in_im + (f * (long long)N + tid) : nullptr;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     using G = Geom<NL>;
     using F = SpectrumFrame<NL, S, IN, OUT>;
     constexpr int T = G::T, E = G::E, FPC = G::FPC, N = NL * S;
-    static_assert(!STAGED || (F::PREFETCH && S == 1), "staging is for the integer formats");
+    static_assert(!STAGED || (S == 1 && (IN == FMT_S8 || IN == FMT_U8 || IN == FMT_S16LE)), "staging is for the integer formats");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_chunk[2];
     __shared__ __align__(8) unsigned long long s_mbar[2];
@@ -607,8 +609,12 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
             chunk_block<NL, FPC, BPS>(p.nframes, q, &f0, &bytes);
             mbar_wait(&s_mbar[it & 1], (uint32_t)((it >> 1) & 1));
             if (active) {
-                F::load_raw((const char *)(stage + (it & 1) * CHUNK_BYTES) + ((f - f0) * (long long)NL + tid) * BPS, raw);
-                F::first_from_raw(raw, wreg, u);
+                if constexpr (F::PREFETCH) {
+                    F::load_raw((const char *)(stage + (it & 1) * CHUNK_BYTES) + ((f - f0) * (long long)NL + tid) * BPS, raw);
+                    F::first_from_raw(raw, wreg, u);
+                } else {  // 32 points per thread: convert straight out of the staged chunk
+                    F::first(p, f, c, tid, wreg, u, (const char *)(stage + (it & 1) * CHUNK_BYTES) + (f - f0) * (long long)NL * BPS);
+                }
             }
             if (q_next2 < nchunks) {
                 chunk_block<NL, FPC, BPS>(p.nframes, q_next2, &f0, &sn.bytes);
