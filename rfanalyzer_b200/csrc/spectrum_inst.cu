@@ -259,12 +259,15 @@ cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc
         if (L.in_fmt == FMT_CF32) return launch_one<NL, S, FMT_CF32, OUT_CPLX>(L, query, grid, spc);
         return cudaErrorInvalidValue;
     }
-    if constexpr (S == 1 && NL >= 1024 && NL <= 4096) {
+    if constexpr (S == 1 && NL >= 1024 && NL <= 8192) {
         if (staged_enabled(L.p.in)) {
             switch (L.in_fmt) {
                 case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB, true>(L, query, grid, spc);
                 case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB, true>(L, query, grid, spc);
-                case FMT_S16LE: return launch_one<NL, S, FMT_S16LE, OUT_DB, true>(L, query, grid, spc);
+                case FMT_S16LE:
+                    if constexpr (NL <= 4096)  // at 8192 two 32 KB chunk buffers no longer fit beside the frames and tables
+                        return launch_one<NL, S, FMT_S16LE, OUT_DB, true>(L, query, grid, spc);
+                    break;
             }
         }
     }
