@@ -70,6 +70,12 @@ int rfa_ctx_sm_count(const rfa_ctx *ctx);
 void *rfa_ctx_stream(const rfa_ctx *ctx);
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 long long rfa_ctx_launch_count(const rfa_ctx *ctx);
+/* Knobs of a context (csrc/tuning.h lists them: "staged", "pdl", "max_grid", "fs_batch_kib", "fs_tma", "fs_ztma",
+ * "fs_pdl", "chunk_kib", "rs_span", "cluster").  The defaults are the product; the knobs exist for A/B timing
+ * runs and for tests that compare two code paths.  Nothing in the library reads the environment.  Unknown names
+ * (including the experimental-kernel options that only librfa_b200_lab.so carries) return RFA_ERR_UNSUPPORTED. */
+int rfa_ctx_set_option(rfa_ctx *ctx, const char *name, long long value);
+int rfa_ctx_get_option(rfa_ctx *ctx, const char *name, long long *value);
 /* pinned host memory, so RFA_MEM_HOST calls copy at full PCIe rate and overlap */
 int rfa_host_alloc(size_t bytes, void **out);
 int rfa_host_free(void *p);

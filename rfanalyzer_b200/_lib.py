@@ -7,8 +7,11 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# RFA_B200_LIB: load a tuning variant of the same library (kernel experiments); never a fallback
+# RFA_B200_LIB: load another build of the same library (librfa_b200_lab.so with the experimental kernels, or a
+# -D tuning variant); never a fallback.  This is the only environment variable the package reads -- the library
+# itself reads none (its knobs are rfa_ctx_set_option).
 LIB_PATH = os.environ.get("RFA_B200_LIB") or os.path.join(HERE, "lib", "librfa_b200.so")
+LAB_LIB_PATH = os.path.join(HERE, "lib", "librfa_b200_lab.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = range(5)
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -88,6 +91,8 @@ SIGNATURES = {
     "rfa_ctx_sm_count": (_i, [_vp]),
     "rfa_ctx_stream": (_vp, [_vp]),
     "rfa_ctx_launch_count": (_ll, [_vp]),
+    "rfa_ctx_set_option": (_i, [_vp, C.c_char_p, _ll]),
+    "rfa_ctx_get_option": (_i, [_vp, C.c_char_p, _pll]),
     "rfa_host_alloc": (_i, [C.c_size_t, _pvp]),
     "rfa_host_free": (_i, [_vp]),
     "rfa_convert": (_i, [_vp, _i, _vp, _ll, _vp, _vp, _i]),

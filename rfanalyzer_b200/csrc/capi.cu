@@ -131,18 +131,24 @@ int rfa_ctx_create(int device, void *stream, rfa_ctx **out) {
     rfa_ctx *c = new rfa_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    // any failure below releases what was created so far (rfa_ctx_destroy copes with half-built contexts)
+    auto fail = [&](cudaError_t e, const char *what) {
+        rfa_ctx_destroy(c);
+        return cuda_fail(e, what);
+    };
+    cudaError_t e2;
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
-        RFA_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        if ((e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e2, "cudaStreamCreate");
         c->own_stream = true;
     }
-    RFA_CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-    RFA_CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    if ((e2 = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)) != cudaSuccess) return fail(e2, "cudaStreamCreate");
+    if ((e2 = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail(e2, "cudaStreamCreate");
     for (int i = 0; i < 2; i++) {
-        RFA_CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
-        RFA_CK(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
-        RFA_CK(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+        if ((e2 = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e2, "cudaEventCreate");
+        if ((e2 = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e2, "cudaEventCreate");
+        if ((e2 = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e2, "cudaEventCreate");
     }
     *out = c;
     return RFA_OK;
@@ -151,19 +157,19 @@ int rfa_ctx_create(int device, void *stream, rfa_ctx **out) {
 int rfa_ctx_destroy(rfa_ctx *c) {
     if (!c) return RFA_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &kv : c->twiddles) cudaFree(kv.second);
     for (auto &kv : c->windows) cudaFree(kv.second);
     if (c->synth_table) cudaFree(c->synth_table);
     for (auto &b : c->stage) b.release();
     for (int i = 0; i < 2; i++) {
-        cudaEventDestroy(c->ev_in[i]);
-        cudaEventDestroy(c->ev_k[i]);
-        cudaEventDestroy(c->ev_out[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
-    cudaStreamDestroy(c->s_in);
-    cudaStreamDestroy(c->s_out);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RFA_OK;
 }
@@ -177,6 +183,64 @@ int rfa_ctx_device(const rfa_ctx *c) { return c ? c->device : -1; }
 int rfa_ctx_sm_count(const rfa_ctx *c) { return c ? c->num_sms : 0; }
 void *rfa_ctx_stream(const rfa_ctx *c) { return c ? (void *)c->stream : nullptr; }
 long long rfa_ctx_launch_count(const rfa_ctx *c) { return c ? c->launches : 0; }
+
+// the context's knobs (tuning.h): name -> field
+static long long *option_slot(rfa::Tuning &t, const char *name, long long *scratch, int **as_int) {
+    *as_int = nullptr;
+    struct IntOpt { const char *name; int rfa::Tuning::*field; };
+    static const IntOpt ints[] = {{"staged", &rfa::Tuning::staged},     {"pdl", &rfa::Tuning::pdl},
+                                  {"max_grid", &rfa::Tuning::max_grid}, {"fs_tma", &rfa::Tuning::fs_tma},
+                                  {"fs_ztma", &rfa::Tuning::fs_ztma},   {"fs_pdl", &rfa::Tuning::fs_pdl},
+                                  {"chunk_kib", &rfa::Tuning::chunk_kib}, {"rs_span", &rfa::Tuning::rs_span},
+                                  {"cluster", &rfa::Tuning::cluster},
+#ifdef RFA_LAB
+                                  {"kernel", &rfa::Tuning::kernel},     {"fourstep", &rfa::Tuning::fourstep},
+                                  {"fs_fused", &rfa::Tuning::fs_fused},
+#endif
+    };
+    for (const IntOpt &o : ints)
+        if (!strcmp(name, o.name)) {
+            *as_int = &(t.*(o.field));
+            return scratch;
+        }
+    if (!strcmp(name, "fs_batch_kib")) return &t.fs_batch_kib;
+#ifdef RFA_LAB
+    if (!strcmp(name, "fs_ring_kib")) return &t.fs_ring_kib;
+#endif
+    return nullptr;
+}
+
+int rfa_ctx_set_option(rfa_ctx *c, const char *name, long long value) {
+    RFA_REQUIRE(c && name, "rfa_ctx_set_option: NULL argument");
+    long long scratch = 0;
+    int *as_int = nullptr;
+    long long *slot = option_slot(c->tune, name, &scratch, &as_int);
+    if (!slot) {
+        set_error("unknown option '%s' (lab-only options need librfa_b200_lab.so)", name);
+        return RFA_ERR_UNSUPPORTED;
+    }
+    RFA_REQUIRE(value >= 0 && value <= 0x7FFFFFFFLL, "option '%s': value %lld out of range", name, value);
+    RFA_REQUIRE(strcmp(name, "fs_batch_kib") || value >= 1, "fs_batch_kib must be at least 1");
+    RFA_REQUIRE(strcmp(name, "chunk_kib") || value >= 1, "chunk_kib must be at least 1");
+    if (as_int)
+        *as_int = (int)value;
+    else
+        *slot = value;
+    return RFA_OK;
+}
+
+int rfa_ctx_get_option(rfa_ctx *c, const char *name, long long *value) {
+    RFA_REQUIRE(c && name && value, "rfa_ctx_get_option: NULL argument");
+    long long scratch = 0;
+    int *as_int = nullptr;
+    long long *slot = option_slot(c->tune, name, &scratch, &as_int);
+    if (!slot) {
+        set_error("unknown option '%s' (lab-only options need librfa_b200_lab.so)", name);
+        return RFA_ERR_UNSUPPORTED;
+    }
+    *value = as_int ? *as_int : *slot;
+    return RFA_OK;
+}
 
 int rfa_host_alloc(size_t bytes, void **out) {
     RFA_REQUIRE(out != nullptr, "rfa_host_alloc: out is NULL");
@@ -290,6 +354,7 @@ static int fft_generic(rfa_ctx *c, int in_kind, int out_kind, const float *in_a,
     L.out_kind = out_kind;
     L.stream = c->stream;
     L.num_sms = c->num_sms;
+    L.tune = c->tune;
     const int nl = n > 16384 ? 16384 : n;
     if (int rc = c->get_twiddles(nl, &L.p.tw)) return rc;
     if (n > 16384)
@@ -384,6 +449,7 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
     L.out_kind = OUT_DB;
     L.stream = c->stream;
     L.num_sms = c->num_sms;
+    L.tune = c->tune;
     L.p.in = iq;
     L.p.win = pl->win;
     L.p.tw = pl->tw;
@@ -408,7 +474,7 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
         RFA_CK(cudaGetLastError());
         c->launches++;
     }
-    if (fourstep_supported(n, pl->d.format, OUT_DB)) {
+    if (fourstep_supported(n, pl->d.format, OUT_DB, c->tune)) {
         // N = 32768 / 65536: column transforms, twiddle, row transforms through an intermediate buffer
         // (fourstep_kernel.cuh); the time average is a row reduction afterwards.  Measured on B200 the fixed cost
         // of a launch pair (persistent-CTA prologue and tail) outweighs keeping the intermediate inside L2:
@@ -417,8 +483,7 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
         if (int rc = c->get_twiddles(n / 256, &fs.tw_n1)) return rc;
         if (int rc = c->get_twiddles(256, &fs.tw_256)) return rc;
         fs.tw_n = pl->twN;
-        const char *eb = getenv("RFA_FS_BATCH_KIB");  // tuning runs and the multi-batch test; read per call
-        long long want = (long long)(eb && atoi(eb) > 0 ? atoi(eb) : 128 << 10) << 10;  // default: 128 MiB per batch
+        long long want = c->tune.fs_batch_kib << 10;  // knob "fs_batch_kib"; default: 128 MiB per batch
         const long long all = nframes * (long long)n * (long long)sizeof(cf);
         if (want > all) want = all;
         if (want < (long long)n * (long long)sizeof(cf)) want = (long long)n * (long long)sizeof(cf);
@@ -559,10 +624,7 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
     const size_t frame_in = (size_t)n * bps, frame_out = (size_t)n * sizeof(float);
     // IQ bytes per chunk: small enough that the first copy in and the last copy out (which overlap with
     // nothing) are short, large enough that the per-chunk launch and copy set-up costs stay hidden
-    static const size_t chunk_bytes = [] {
-        const char *e = getenv("RFA_CHUNK_KIB");  // tuning runs
-        return (size_t)(e && atoi(e) > 0 ? atoi(e) : 4096) << 10;
-    }();
+    const size_t chunk_bytes = (size_t)c->tune.chunk_kib << 10;  // knob "chunk_kib", default 4 MiB
     long long cf_frames = (long long)(chunk_bytes / frame_in);
     if (cf_frames < L + 1) cf_frames = L + 1;
     if (cf_frames > nframes) cf_frames = nframes;
@@ -581,6 +643,15 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
         if (o->peaks_accumulate)
             RFA_CK(cudaMemcpyAsync(dpeaks, o->peaks, frame_out, cudaMemcpyHostToDevice, c->stream));
     }
+    // no early return may leave copies into / out of the caller's buffers in flight
+    struct DrainOnExit {
+        rfa_ctx *c;
+        ~DrainOnExit() {
+            cudaStreamSynchronize(c->s_in);
+            cudaStreamSynchronize(c->s_out);
+            cudaStreamSynchronize(c->stream);
+        }
+    } drain{c};
     // make the side streams start after whatever is already queued on the context stream
     RFA_CK(cudaEventRecord(c->ev_k[0], c->stream));
     RFA_CK(cudaEventRecord(c->ev_k[1], c->stream));

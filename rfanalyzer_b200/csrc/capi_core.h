@@ -12,6 +12,7 @@
 
 #include "../../include/rfa_b200.h"
 #include "rfa_fft_core.cuh"
+#include "tuning.h"
 
 namespace rfa {
 
@@ -53,6 +54,7 @@ struct rfa_ctx {
     bool own_stream = false;
     int num_sms = 0;
     long long launches = 0;
+    rfa::Tuning tune;                                 // rfa_ctx_set_option
     // pipelined host-memory mode: copy engines run beside the compute stream
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};

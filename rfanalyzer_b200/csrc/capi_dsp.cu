@@ -143,7 +143,7 @@ static int resampler_run(rfa_resampler *r, StreamDesc in, long long n, float *ou
     if (nout > capacity) nout = capacity;
     r->h.attach(in);
     cudaError_t e = resample_launch(in, r->bank.as<float>(), r->I, r->D, r->nt, r->rel, r->ph, nout, out_re, out_im,
-                                    r->exact, c->stream);
+                                    r->exact, c->stream, c->tune.rs_span);
     if (e != cudaSuccess) return cuda_fail(e, "resample kernel");
     if (nout > 0) c->launches++;
     const long long T = (long long)r->ph + nout * r->D;
@@ -436,6 +436,9 @@ struct rfa_chain {
     Buf fm_carry, agc_state, agc_scratch, seg;
     DevF q_re, q_im, u_re, u_im, b_re, b_im, dem, a1, a2;
     Buf s_iq, s_audio;
+    // rfa_chain_process advances the streaming state stage by stage; a failure in the middle of a call leaves
+    // the stages out of step, so the chain refuses further packets until rfa_chain_seek re-positions it
+    bool poisoned = false;
 };
 
 extern "C" {
@@ -623,6 +626,7 @@ int rfa_chain_seek(rfa_chain *ch, long long sample_index, long long *audio_index
             }
         }
     }
+    ch->poisoned = false;
     if (audio_index) *audio_index = produced;
     return RFA_OK;
 }
@@ -635,8 +639,14 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
     if (nsamples == 0) return RFA_OK;
     RFA_REQUIRE(iq && audio, "rfa_chain_process: NULL buffer");
     RFA_REQUIRE(capacity >= rfa_chain_max_audio(ch, nsamples), "audio buffer too small: need rfa_chain_max_audio()");
+    RFA_REQUIRE(!ch->poisoned, "an earlier rfa_chain_process failed half way: call rfa_chain_seek to re-position the chain");
     rfa_ctx *c = ch->ctx;
     if (int rc = c->use()) return rc;
+    struct Guard {  // set until the call has run to its end
+        rfa_chain *ch;
+        bool ok = false;
+        ~Guard() { ch->poisoned = !ok; }
+    } guard{ch};
     const int P = ch->d.packet_samples, mode = ch->d.mode;
     const int bps = ch->d.format == RFA_FMT_S16LE ? 4 : 2;
     const long long npk = (nsamples + P - 1) / P;
@@ -779,6 +789,7 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
     // the segment table was staged from a host vector that dies with this call
     RFA_CK(cudaStreamSynchronize(c->stream));
     *n_audio = nfinal;
+    guard.ok = true;
     return RFA_OK;
 }
 

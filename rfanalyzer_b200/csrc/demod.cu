@@ -134,14 +134,16 @@ __global__ void __launch_bounds__(256) agc_scan_kernel(const long long *off, int
 template <bool SUBTRACT_MEAN>
 __global__ void __launch_bounds__(256) normalise_kernel(float *__restrict__ x, const long long *__restrict__ off,
                                                         const float *__restrict__ gain, const float *__restrict__ mean,
-                                                        float volume) {
-    const int p = blockIdx.y;
-    const float g = gain[p], m = SUBTRACT_MEAN ? mean[p] : 0.0f;
-    const long long b = off[p], e = off[p + 1];
-    for (long long i = b + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (long long)gridDim.x * blockDim.x) {
-        float v = x[i];
-        if (SUBTRACT_MEAN) v = __fsub_rn(v, m);
-        x[i] = __fmul_rn(__fmul_rn(v, g), volume);
+                                                        float volume, int npackets) {
+    // gridDim.y is capped at 65535 by CUDA: a block row strides over the packets
+    for (int p = blockIdx.y; p < npackets; p += gridDim.y) {
+        const float g = gain[p], m = SUBTRACT_MEAN ? mean[p] : 0.0f;
+        const long long b = off[p], e = off[p + 1];
+        for (long long i = b + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (long long)gridDim.x * blockDim.x) {
+            float v = x[i];
+            if (SUBTRACT_MEAN) v = __fsub_rn(v, m);
+            x[i] = __fmul_rn(__fmul_rn(v, g), volume);
+        }
     }
 }
 
@@ -185,11 +187,11 @@ cudaError_t agc_launch(float *x, const long long *off, int npackets, long long m
     unsigned bx = (unsigned)((max_packet + 255) / 256);
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
-    dim3 grid(bx, (unsigned)npackets);
+    dim3 grid(bx, (unsigned)(npackets < 65535 ? npackets : 65535));
     if (subtract_mean)
-        normalise_kernel<true><<<grid, 256, 0, st>>>(x, off, gain, mean, volume);
+        normalise_kernel<true><<<grid, 256, 0, st>>>(x, off, gain, mean, volume, npackets);
     else
-        normalise_kernel<false><<<grid, 256, 0, st>>>(x, off, gain, mean, volume);
+        normalise_kernel<false><<<grid, 256, 0, st>>>(x, off, gain, mean, volume, npackets);
     return cudaGetLastError();
 }
 

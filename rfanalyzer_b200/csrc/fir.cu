@@ -465,7 +465,7 @@ static StreamSrc make_src(const StreamDesc &d) {
 }
 
 cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int D, int nt, long long rel, int ph0,
-                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st) {
+                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st, int rs_span) {
     if (nout <= 0) return cudaSuccess;
     if (nt + 2 > kSpanMax) return cudaErrorInvalidValue;
     ResampleArgs a{};
@@ -492,11 +492,7 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
     if (!exact && aligned && A >= 2 && A <= 12 && (size_t)I * D * 12 <= 8192) {
         // register-tiled path: M = 9 outputs per thread, B blocks per phase
         constexpr int M = 9, kSpanT = 4096;  // 4 K samples per CTA: six CTAs per SM overlap staging and dot products
-        static const int span_env = [] {  // tuning runs: samples staged per CTA
-            const char *e = getenv("RFA_RS_SPAN");
-            return e && atoi(e) > 0 ? atoi(e) : 0;
-        }();
-        const int span_cap = span_env > 0 && span_env < kSpanT ? span_env : kSpanT;
+        const int span_cap = rs_span > 0 && rs_span < kSpanT ? rs_span : kSpanT;  // tuning knob "rs_span"
         const int amax = A <= 3 ? 3 : (A <= 5 ? 5 : (A <= 9 ? 9 : 12));
         long long B = ((long long)span_cap - 8 - (long long)(amax + 1) * D) / ((long long)M * D);  // span <= (B*M + amax + 1)*D + 4
         if (B >= 16) B -= B % 16;

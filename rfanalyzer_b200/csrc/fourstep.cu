@@ -37,10 +37,9 @@ EncodeTiledFn encode_tiled() {
 
 // the IQ bytes of a call as a [frames * N1][256 * bps] byte matrix, box = one column group of one frame
 template <int N1>
-bool make_input_map(const void *iq, long long nframes, int bps, CUtensorMap *tm) {
+bool make_input_map(const void *iq, long long nframes, int bps, CUtensorMap *tm, const Tuning &tune) {
     using G = GeomFS<N1>;
-    const char *e = getenv("RFA_FS_TMA");  // RFA_FS_TMA=0: per-thread loads (A/B timing runs, the fallback's test)
-    if (e && atoi(e) == 0) return false;
+    if (!tune.fs_tma) return false;  // knob "fs_tma" = 0: per-thread loads (A/B timing runs, the fallback's test)
     EncodeTiledFn enc = encode_tiled();
     if (!enc || ((size_t)iq & 15) != 0 || nframes * N1 > 0x7FFFFFFFLL) return false;  // box coordinates are 32-bit signed
     const cuuint64_t dims[2] = {(cuuint64_t)256 * bps, (cuuint64_t)nframes * N1};
@@ -53,16 +52,16 @@ bool make_input_map(const void *iq, long long nframes, int bps, CUtensorMap *tm)
 
 thread_local int g_last_launches = 0;
 
+#ifdef RFA_LAB
 // One cooperative launch for the whole call (fourstep_fused_kernel).  Returns cudaErrorNotSupported when the
 // configuration does not allow it; the caller then runs the two-kernel path.
 template <int N1, int IN>
 cudaError_t run_fused(const SpectrumLaunch &L, const FourStepLaunch &fs, const CUtensorMap &tmap) {
     using G = GeomFS<N1>;
     constexpr int BPS = in_elem_bytes<IN>();
-    // RFA_FS_FUSED=1 selects this path.  Measured on B200 it is correct but SLOWER than two kernels per batch
+    // Lab builds only (knob "fs_fused").  Measured on B200 it is correct but SLOWER than two kernels per batch
     // (2^24 samples: 119 / 125 us against 77 / 81 us, gpurun_out/fs_timing5.log), so it is not the default.
-    const char *ef = getenv("RFA_FS_FUSED");
-    if (!(ef && atoi(ef) == 1) || !fs.sync || L.p.nframes > 0x7FFFFFFFLL) return cudaErrorNotSupported;
+    if (!L.tune.fs_fused || !fs.sync || L.p.nframes > 0x7FFFFFFFLL) return cudaErrorNotSupported;
     auto kf = fourstep_fused_kernel<N1, IN>;
     const size_t smem = G::smem_fused(BPS);
     static thread_local int dev_done = -1, occ = 0, coop = 0;
@@ -79,8 +78,7 @@ cudaError_t run_fused(const SpectrumLaunch &L, const FourStepLaunch &fs, const C
     // one producer and one consumer CTA per SM, rounded down to whole lanes
     const int lanes_a = L.num_sms / G::GROUPS_A, lanes_b = L.num_sms / G::GROUPS_B;
     if (!coop || occ < 2 || lanes_a < 1 || lanes_b < 1) return cudaErrorNotSupported;
-    const char *er = getenv("RFA_FS_RING_KIB");  // Z ring size (tuning runs); default 32 MiB: a quarter of the L2
-    const long long ring_bytes = (long long)(er && atoi(er) > 0 ? atoi(er) : 32 << 10) << 10;
+    const long long ring_bytes = L.tune.fs_ring_kib << 10;  // Z ring size; default 32 MiB: a quarter of the L2
     long long ring = ring_bytes / ((long long)G::N * (long long)sizeof(cf));
     const long long min_ring = 2LL * lanes_b + lanes_a + 8;  // the consumers' look-ahead must stay inside the ring
     if (ring < min_ring) ring = min_ring;
@@ -114,13 +112,13 @@ cudaError_t run_fused(const SpectrumLaunch &L, const FourStepLaunch &fs, const C
     if (e == cudaSuccess) g_last_launches = 1;
     return e;
 }
+#endif  // RFA_LAB
 
 // the batch buffer Z as a [frames * N1][512] float matrix, box = the N1 x CPC points one column group finishes per frame
 template <int N1>
-bool make_z_map(cf *z, long long batch_frames, CUtensorMap *tm) {
+bool make_z_map(cf *z, long long batch_frames, CUtensorMap *tm, const Tuning &tune) {
     using G = GeomFS<N1>;
-    const char *e = getenv("RFA_FS_ZTMA");  // RFA_FS_ZTMA=0: per-thread stores of Z (A/B timing runs)
-    if (e && atoi(e) == 0) return false;
+    if (!tune.fs_ztma) return false;  // knob "fs_ztma" = 0: per-thread stores of Z (A/B timing runs)
     EncodeTiledFn enc = encode_tiled();
     if (!enc || ((size_t)z & 15) != 0 || batch_frames * N1 > 0x7FFFFFFFLL) return false;
     const cuuint64_t dims[2] = {512, (cuuint64_t)batch_frames * N1};
@@ -137,14 +135,16 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     constexpr int BPS = in_elem_bytes<IN>();
     alignas(64) CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    const bool staged = make_input_map<N1>(L.p.in, L.p.nframes, BPS, &tmap);
+    const bool staged = make_input_map<N1>(L.p.in, L.p.nframes, BPS, &tmap, L.tune);
     auto ka = staged ? fourstep_cols_kernel<N1, IN, true> : fourstep_cols_kernel<N1, IN, false>;
     auto kb = fourstep_rows_kernel<N1>;
     const size_t smem_a = staged ? G::smem_a_staged(BPS) : G::SMEM_A;
+#ifdef RFA_LAB
     if (staged) {
         const cudaError_t ef = run_fused<N1, IN>(L, fs, tmap);
         if (ef != cudaErrorNotSupported) return ef;
     }
+#endif
     g_last_launches = 0;
     static thread_local int dev_done[2] = {-1, -1}, occ_as[2] = {1, 1}, occ_b = 1;  // per instantiation <N1, IN>, per device
     int dev = 0;
@@ -164,7 +164,7 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     memset(&tmap_z, 0, sizeof(tmap_z));
     // measured (gpurun_out/fs_timing6.log): 2.5 % faster for 8-bit IQ, 8 % slower for int16 IQ, whose raw tiles are
     // twice as large (the store tile then costs the second resident CTA its shared memory head-room)
-    const bool ztma = staged && BPS == 2 && make_z_map<N1>(fs.z, batch, &tmap_z);
+    const bool ztma = staged && BPS == 2 && make_z_map<N1>(fs.z, batch, &tmap_z, L.tune);
     auto kz = fourstep_cols_ztma_kernel<N1, IN>;
     const size_t smem_z = G::smem_a_zstore(BPS);
     static thread_local int dev_done_z = -1, occ_z = 1;
@@ -173,8 +173,7 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
         if (e != cudaSuccess) return e;
         dev_done_z = dev;
     }
-    const char *ep = getenv("RFA_FS_PDL");  // RFA_FS_PDL=0: plain stream order (A/B timing runs)
-    const bool pdl = !(ep && atoi(ep) == 0);
+    const bool pdl = L.tune.fs_pdl != 0;  // knob "fs_pdl" = 0: plain stream order (A/B timing runs)
     FourStepParams a{};
     a.p = L.p;
     a.tw_n1 = fs.tw_n1;
@@ -226,9 +225,12 @@ cudaError_t run_fmt(const SpectrumLaunch &L, const FourStepLaunch &fs) {
 
 }  // namespace
 
-bool fourstep_supported(int N, int in_fmt, int out_kind) {
-    const char *e = getenv("RFA_FOURSTEP");  // RFA_FOURSTEP=0: the residue-split kernel (A/B timing runs)
-    if (e && atoi(e) == 0) return false;
+bool fourstep_supported(int N, int in_fmt, int out_kind, const Tuning &tune) {
+#ifdef RFA_LAB
+    if (!tune.fourstep) return false;  // lab knob "fourstep" = 0: the residue-split kernel, a second factorisation
+#else
+    (void)tune;
+#endif
     return (N == 32768 || N == 65536) && out_kind == OUT_DB && (in_fmt == FMT_S8 || in_fmt == FMT_U8 || in_fmt == FMT_S16LE);
 }
 

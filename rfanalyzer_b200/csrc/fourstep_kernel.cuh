@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(256) fourstep_rows_kernel(const FourStepParams
     fourstep_rows_cta<N1, false>(a, (int)blockIdx.x, (int)gridDim.x, smem_raw, s_mbar);
 }
 
+#ifdef RFA_LAB  // lab builds only: slower than the two-kernel path, and its hand-over watchdog traps the context
 // Both steps in ONE cooperative launch (all CTAs co-resident): CTAs 0 .. n_prod-1 produce column transforms into
 // a ring of Z frames that fits the L2, the others consume them as row transforms, frame by frame, handing over
 // through per-frame counters.  Z never travels to HBM, the two steps overlap on every SM (one is store-, the
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(256, 2) fourstep_fused_kernel(const FourStepPa
     else
         fourstep_rows_cta<N1, true>(a, (int)blockIdx.x - a.n_prod, (int)gridDim.x - a.n_prod, smem_raw, s_mbar);
 }
+#endif  // RFA_LAB
 #endif  // __CUDACC__
 
 }  // namespace rfa

@@ -22,7 +22,7 @@ struct StreamDesc {
     int nco_len = 1, nco_idx = 0;
 };
 cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int D, int nt, long long rel, int ph0,
-                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st);
+                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st, int rs_span = 0);
 cudaError_t fir_launch(const StreamDesc &in, const float *taps_re, const float *taps_im, int ntaps, int dec,
                        long long first, long long nout, bool real_only, float *out_re, float *out_im, bool exact,
                        cudaStream_t st);

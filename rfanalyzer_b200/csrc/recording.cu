@@ -212,7 +212,11 @@ int rfa_spectrum_process_file(rfa_spectrum_plan *plan, const char *path, long lo
     }
     fseeko(fp, 0, SEEK_END);
     const long long file_frames = (long long)ftello(fp) / frame_bytes;
-    RFA_REQUIRE(first_frame >= 0 && first_frame <= file_frames, "first frame %lld outside the file (%lld frames)", first_frame, file_frames);
+    if (first_frame < 0 || first_frame > file_frames) {
+        fclose(fp);
+        set_error("first frame %lld outside the file (%lld frames)", first_frame, file_frames);
+        return RFA_ERR_INVALID;
+    }
     long long total = file_frames - first_frame;
     if (nframes >= 0 && nframes < total) total = nframes;
     if (total == 0) {

@@ -1,13 +1,16 @@
 // spectrum_inst.cu -- instantiations of the fused spectrum kernel, compiled once per
 // size group (-DRFA_GROUP=0..3) so the groups build in parallel.
+//
+// RFA_LAB (librfa_b200_lab.so, `make lab`) adds the experimental N = 4096 kernels that measured slower than the default
+// (dual-frame, 64 x 64, anti-phase pair, lean) behind the context knob "kernel", and the residue split for integer input.
 #include "device_once.h"
+#include "spectrum_launch.h"
+#ifdef RFA_LAB
 #include "spectrum_pair_kernel.cuh"
 #include "spectrum_lean_kernel.cuh"
-#include <stdlib.h>
-
-#include "spectrum_launch.h"
 #include "spectrum2_kernel.cuh"
 #include "spectrum64_kernel.cuh"
+#endif
 
 namespace rfa {
 namespace {
@@ -35,11 +38,7 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     long long need = ((L.p.nframes + G::FPC - 1) / G::FPC) * S;
     if (need / S > 0x7FFF0000LL) return cudaErrorInvalidValue;  // chunk indices are 32-bit in the kernel
     long long cap = (long long)L.num_sms * occ;
-    static const int maxgrid_env = [] {  // tuning runs only
-        const char *e = getenv("RFA_MAXGRID");
-        return e ? atoi(e) : 0;
-    }();
-    if (maxgrid_env > 0 && maxgrid_env < cap) cap = maxgrid_env;
+    if (L.tune.max_grid > 0 && L.tune.max_grid < cap) cap = L.tune.max_grid;  // knob "max_grid" (occupancy experiments)
     if (L.max_grid > 0 && L.max_grid < cap) cap = L.max_grid;
     // the averaging CTA (spectrum_kernel.cuh: average_cta) takes one resident slot
     const bool avg_cta = OUT == OUT_DB && L.p.avg != nullptr;
@@ -53,9 +52,8 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
     if (query) return cudaSuccess;
     if (avg_cta) grid += 1;
     {
-        // back-to-back launches overlap: programmatic stream serialization + griddepcontrol in the kernel (RFA_PDL=0: off)
-        const char *e = getenv("RFA_PDL");
-        if (!(e && atoi(e) == 0)) {
+        // back-to-back launches overlap: programmatic stream serialization + griddepcontrol in the kernel (knob "pdl" = 0: off)
+        if (L.tune.pdl) {
             SpectrumParams pp = L.p;
             pp.pdl = 1;
             cudaLaunchAttribute attr[1];
@@ -76,12 +74,10 @@ cudaError_t launch_one(const SpectrumLaunch &L, bool query, int *grid_out, int *
 }
 
 // TMA-staged input (spectrum_kernel.cuh, STAGED): N = 1024 .. 4096, integer formats, 16-byte aligned IQ.
-// RFA_STAGED=0 switches it off (A/B timing runs).
-static bool staged_enabled(const void *iq) {
-    const char *e = getenv("RFA_STAGED");
-    return !(e && atoi(e) == 0) && ((size_t)iq & 15) == 0;
-}
+// The knob "staged" = 0 switches it off (A/B timing runs).
+static bool staged_enabled(const SpectrumLaunch &L) { return L.tune.staged && ((size_t)L.p.in & 15) == 0; }
 
+#ifdef RFA_LAB
 // dual-frame kernel (spectrum2_kernel.cuh): one 256-thread CTA per SM, two frames per thread
 template <int NL, int IN>
 cudaError_t launch_two(const SpectrumLaunch &L, bool query, int *grid_out, int *spc_out) {
@@ -195,50 +191,27 @@ cudaError_t launch_lean(const SpectrumLaunch &L, bool query, int *grid_out, int 
     kern<<<(unsigned)grid, G::CTA, SMEM, L.stream>>>(L.p);
     return cudaGetLastError();
 }
-static bool lean_enabled(const void *iq) {
-    const char *e = getenv("RFA_LEAN");  // read at every launch so that tests and timing runs can switch
-    return e && atoi(e) == 1 && ((size_t)iq & 15) == 0;
-}
-
-static bool pair_enabled(const void *iq) {
-    const char *e = getenv("RFA_PAIR");  // read at every launch so that tests and timing runs can switch
-    return e && atoi(e) == 1 && ((size_t)iq & 15) == 0;
-}
-
-static bool k64_enabled() {
-    const char *e = getenv("RFA_K64");
-    return e && atoi(e) == 1;
-}
-
-// RFA_DUAL=1 selects the dual-frame kernel for N = 256 .. 4096 (read at every launch so that tests
-// and timing runs can switch).  Default: the single-frame kernel, which is ahead on B200 for now
-// (gpurun_out/timing17.log: 45.5 us vs 47.5 us per 2^24 samples at N = 4096).
-static bool dual_enabled() {
-    const char *e = getenv("RFA_DUAL");
-    return e && atoi(e) == 1;
-}
+#endif  // RFA_LAB
 
 template <int NL, int S>
 cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc) {
+#ifdef RFA_LAB
+    const bool al16 = ((size_t)L.p.in & 15) == 0;
     if constexpr (S == 1 && NL == 4096) {
-        if (L.out_kind == OUT_DB && !query && k64_enabled() && L.p.avg == nullptr && L.p.twN != nullptr) {
+        if (L.out_kind == OUT_DB && !query && L.tune.kernel == 2 && L.p.avg == nullptr && L.p.twN != nullptr) {
             switch (L.in_fmt) {
                 case FMT_S8: return launch_64<FMT_S8>(L);
                 case FMT_U8: return launch_64<FMT_U8>(L);
                 case FMT_S16LE: return launch_64<FMT_S16LE>(L);
             }
         }
-    }
-    if constexpr (S == 1 && NL == 4096) {
-        if (L.out_kind == OUT_DB && lean_enabled(L.p.in)) {
+        if (L.out_kind == OUT_DB && L.tune.kernel == 4 && al16) {
             switch (L.in_fmt) {
                 case FMT_S8: return launch_lean<FMT_S8>(L, query, grid, spc);
                 case FMT_U8: return launch_lean<FMT_U8>(L, query, grid, spc);
             }
         }
-    }
-    if constexpr (S == 1 && NL == 4096) {
-        if (L.out_kind == OUT_DB && pair_enabled(L.p.in)) {
+        if (L.out_kind == OUT_DB && L.tune.kernel == 3 && al16) {
             switch (L.in_fmt) {
                 case FMT_S8: return launch_pair<FMT_S8>(L, query, grid, spc);
                 case FMT_U8: return launch_pair<FMT_U8>(L, query, grid, spc);
@@ -247,7 +220,7 @@ cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc
         }
     }
     if constexpr (S == 1 && NL >= 256 && NL <= 4096) {
-        if (L.out_kind == OUT_DB && dual_enabled()) {
+        if (L.out_kind == OUT_DB && L.tune.kernel == 1) {
             switch (L.in_fmt) {
                 case FMT_S8: return launch_two<NL, FMT_S8>(L, query, grid, spc);
                 case FMT_U8: return launch_two<NL, FMT_U8>(L, query, grid, spc);
@@ -255,12 +228,13 @@ cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc
             }
         }
     }
+#endif  // RFA_LAB
     if (L.out_kind == OUT_CPLX) {
         if (L.in_fmt == FMT_CF32) return launch_one<NL, S, FMT_CF32, OUT_CPLX>(L, query, grid, spc);
         return cudaErrorInvalidValue;
     }
     if constexpr (S == 1 && NL >= 1024 && NL <= 8192) {
-        if (staged_enabled(L.p.in)) {
+        if (staged_enabled(L)) {
             switch (L.in_fmt) {
                 case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB, true>(L, query, grid, spc);
                 case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB, true>(L, query, grid, spc);
@@ -272,17 +246,29 @@ cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc
         }
     }
     if constexpr (S == 1 && NL == 16384) {  // 8-bit IQ: two 32 KB chunk buffers fit beside the 139 KB exchange frame
-        if (staged_enabled(L.p.in)) {
+        if (staged_enabled(L)) {
             switch (L.in_fmt) {
                 case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB, true>(L, query, grid, spc);
                 case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB, true>(L, query, grid, spc);
             }
         }
     }
+#ifndef RFA_LAB
+    // the residue split (S > 1) serves float input only (rfa_fft_*, N = 32768 / 65536); integer IQ of those sizes
+    // goes through the cluster / four-step paths, its residue-split instantiations live in the lab build
+    if constexpr (S > 1)
+        if (L.in_fmt == FMT_S8 || L.in_fmt == FMT_U8 || L.in_fmt == FMT_S16LE) return cudaErrorNotSupported;
+#endif
     switch (L.in_fmt) {
+#if defined(RFA_LAB)
         case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB>(L, query, grid, spc);
         case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB>(L, query, grid, spc);
         case FMT_S16LE: return launch_one<NL, S, FMT_S16LE, OUT_DB>(L, query, grid, spc);
+#else
+        case FMT_S8: if constexpr (S == 1) return launch_one<NL, S, FMT_S8, OUT_DB>(L, query, grid, spc); break;
+        case FMT_U8: if constexpr (S == 1) return launch_one<NL, S, FMT_U8, OUT_DB>(L, query, grid, spc); break;
+        case FMT_S16LE: if constexpr (S == 1) return launch_one<NL, S, FMT_S16LE, OUT_DB>(L, query, grid, spc); break;
+#endif
         case FMT_CF32: return launch_one<NL, S, FMT_CF32, OUT_DB>(L, query, grid, spc);
         case FMT_PF32: return launch_one<NL, S, FMT_PF32, OUT_DB>(L, query, grid, spc);
     }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "spectrum_kernel.cuh"
+#include "tuning.h"
 
 namespace rfa {
 
@@ -14,6 +15,7 @@ struct SpectrumLaunch {
     cudaStream_t stream;
     int num_sms;
     int max_grid;  // 0 = size to the machine
+    Tuning tune;   // the context's knobs (rfa_ctx_set_option)
 };
 
 // number of CTAs the launcher will use and the per-CTA frame slots (for peak_partial sizing)
@@ -36,7 +38,7 @@ struct FourStepLaunch {
     long long z_bytes;
     unsigned int *sync;  // 2 * nframes counters for the fused launch (NULL: two kernels per batch)
 };
-bool fourstep_supported(int N, int in_fmt, int out_kind);
+bool fourstep_supported(int N, int in_fmt, int out_kind, const Tuning &tune);
 int fourstep_launches(int N, long long nframes, long long z_bytes);  // of the most recent fourstep_launch on this thread
 cudaError_t fourstep_launch(const SpectrumLaunch &L, const FourStepLaunch &fs);
 

@@ -51,6 +51,30 @@ class Context:
     def sync(self):
         check(self.lib.rfa_ctx_sync(self.handle))
 
+    def set_option(self, name, value):
+        """A knob of this context (rfa_ctx_set_option; csrc/tuning.h).  Returns the previous value."""
+        old = self.get_option(name)
+        check(self.lib.rfa_ctx_set_option(self.handle, name.encode(), int(value)))
+        return old
+
+    def get_option(self, name):
+        v = C.c_longlong()
+        check(self.lib.rfa_ctx_get_option(self.handle, name.encode(), C.byref(v)))
+        return v.value
+
+    def options(self, **kw):
+        """Context manager: set knobs for a block, restore them afterwards."""
+        ctx = self
+
+        class _Scope:
+            def __enter__(self):
+                self.old = {k: ctx.set_option(k, v) for k, v in kw.items()}
+
+            def __exit__(self, *exc):
+                for k, v in self.old.items():
+                    ctx.set_option(k, v)
+        return _Scope()
+
     @property
     def sm_count(self):
         return self.lib.rfa_ctx_sm_count(self.handle)

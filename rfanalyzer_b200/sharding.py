@@ -55,6 +55,7 @@ class ShardedSpectrum:
     def __init__(self, plan, rank=0, world_size=1, group=None):
         self.plan, self.rank, self.world, self.group = plan, rank, world_size, group
         self.n, self.L = plan.fft_size, plan.avg_len
+        self._packed = None
 
     def local_range(self, total_frames):
         return shard_frames(total_frames, self.world, self.rank)
@@ -72,25 +73,40 @@ class ShardedSpectrum:
             self.reduce(total_frames, rows_local, peaks, avg)
 
     def reduce(self, total_frames, rows_local, peaks, avg):
-        """Exchange the two N-float summaries: all_reduce(MAX) of the peak hold, and the average of
-        the newest L+1 rows from the rank(s) that hold them."""
+        """Exchange the two N-float summaries in ONE collective: peaks and the averaged spectrum travel as one
+        2N-float vector through all_reduce(MAX) -- the rank that holds the newest L+1 rows contributes its
+        average, every other rank -inf, so the maximum IS the owner's average (bit for bit) and the peak hold
+        is the element-wise maximum over all ranks (FftProcessor.kt:244).  Only when the newest L+1 rows
+        straddle ranks (fewer than L+1 frames on the last rank) are the ranks' newest rows gathered and summed
+        in the reference's order (AnalyzerSurface.kt:710-714)."""
         if self.world == 1:
             return
         _, nloc = self.local_range(total_frames)
-        dist.all_reduce(peaks, op=dist.ReduceOp.MAX, group=self.group)
         owners = tail_owner_plan(total_frames, self.world, self.L)
+        n = self.n
         if len(owners) == 1 and total_frames >= self.L + 1:
-            dist.broadcast(avg, src=owners[0][0], group=self.group)
+            if self._packed is None or self._packed.device != peaks.device:
+                self._packed = torch.empty(2 * n, dtype=torch.float32, device=peaks.device)
+            packed = self._packed
+            packed[:n].copy_(peaks)
+            if self.rank == owners[0][0]:
+                packed[n:].copy_(avg)
+            else:
+                packed[n:].fill_(float("-inf"))
+            dist.all_reduce(packed, op=dist.ReduceOp.MAX, group=self.group)
+            peaks.copy_(packed[:n])
+            avg.copy_(packed[n:])
             return
+        dist.all_reduce(peaks, op=dist.ReduceOp.MAX, group=self.group)
         # rare: the newest L+1 rows straddle ranks -- gather each rank's newest rows
-        mine = torch.full((self.L + 1, self.n), -9999.0, dtype=torch.float32, device=avg.device)
+        mine = torch.full((self.L + 1, n), -9999.0, dtype=torch.float32, device=avg.device)
         take = min(self.L + 1, nloc)
         if take:
-            mine[:take] = torch.flip(rows_local[nloc - take:nloc, : self.n], dims=[0])
+            mine[:take] = torch.flip(rows_local[nloc - take:nloc, :n], dims=[0])
         gathered = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(gathered, mine, group=self.group)
         tail = assemble_tail(gathered, total_frames, self.world, self.L).contiguous()
-        self.plan.ctx.average_rows(tail, 0, 1, 0, self.n, min(self.L + 1, total_frames), self.L, self.n, avg)
+        self.plan.ctx.average_rows(tail, 0, 1, 0, n, min(self.L + 1, total_frames), self.L, n, avg)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -114,6 +130,24 @@ def default_halo_packets(mode):
     return 1 if mode in (2, 3) else 256  # MODE_NFM, MODE_WFM
 
 
+def delay_line_span(plan):
+    """Input samples that the chain's delay lines reach back: the resampler's taps per phase plus the user
+    filter (27 taps), the SSB / CW band-pass (181 taps, <= 2x decimation) and the two audio decimators (9 taps at
+    the demodulated rate, 13 taps after the first /2) referred to the input rate through D/I.  An upper bound --
+    the halo must cover it or a rank's first audio samples differ from the sequential run."""
+    banded = plan.desc.mode in (4, 5, 6)  # LSB, USB, CW
+    span_q = 26 + (180 if banded else 0) + (8 + 12 * 2) * (2 if banded else 1)
+    ratio = plan.decimation / plan.interpolation
+    return plan.taps_per_phase + int(span_q * ratio + ratio) + 1
+
+
+def halo_packets_for(plan):
+    """Warm-up packets for `plan`: the mode's default, raised until it covers the delay-line span (large
+    decimation with small packets, e.g. 20 Msps -> 48 kHz with 1024-sample packets)."""
+    need = -(-delay_line_span(plan) // plan.desc.packet_samples)
+    return max(default_halo_packets(plan.desc.mode), need)
+
+
 class ShardedChain:
     """One rank's share of a time-sharded demodulation run: seek to a packet boundary one halo before the
     segment, re-process the halo (audio discarded), then the segment.  No collective on the data path: the
@@ -123,7 +157,10 @@ class ShardedChain:
     def __init__(self, plan, rank=0, world_size=1, halo_packets=None, group=None):
         self.plan, self.rank, self.world, self.group = plan, rank, world_size, group
         self.packet = plan.desc.packet_samples
-        self.halo_packets = default_halo_packets(plan.desc.mode) if halo_packets is None else int(halo_packets)
+        self.halo_packets = halo_packets_for(plan) if halo_packets is None else int(halo_packets)
+        if self.halo_packets * self.packet < delay_line_span(plan):
+            raise ValueError("halo of %d packets (%d samples) is shorter than the chain's delay lines (%d samples)"
+                             % (self.halo_packets, self.halo_packets * self.packet, delay_line_span(plan)))
 
     def segment(self, total_samples, rank=None):
         """(halo_start, first, nsamples): the rank needs input samples [halo_start, first + nsamples)."""

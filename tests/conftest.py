@@ -9,6 +9,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# tests/lab exercises the experimental kernels of librfa_b200_lab.so; it is collected only when the package is
+# pointed at that build (tests/test_lab_gpu.py does so in a subprocess)
+collect_ignore_glob = [] if os.environ.get("RFA_B200_LIB", "").endswith("_lab.so") else ["lab/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with `pytest -m gpu`)")
 

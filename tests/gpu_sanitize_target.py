@@ -19,15 +19,19 @@ with torch.cuda.stream(stream):
         ctx.sync()
         peak, mean = ctx.detect_windows(rows, n, n, [(0, 0, n - 1), (frames - 1, 5, 50)])
         print(fmt, n, float(rows.max()), float(peak[0]))
-    for var in ("RFA_PAIR", "RFA_LEAN"):
-        os.environ[var] = "1"
+    for var, kernel in (("pair", 3), ("lean", 4)):   # lab build only (RFA_B200_LIB=.../librfa_b200_lab.so)
+        try:
+            ctx.set_option("kernel", kernel)
+        except rfa.RfaError:
+            print(var, "kernel: not in this build")
+            continue
         plan = rfa.SpectrumPlan(ctx, 0, 4096, avg_len=3)
         iq = torch.from_numpy(O.synth_iq(0, 4096 * 11)).cuda()
         rows = torch.zeros((11, 4096), dtype=torch.float32, device="cuda")
         peaks = torch.zeros(4096, dtype=torch.float32, device="cuda"); avg = torch.zeros(4096, dtype=torch.float32, device="cuda")
         plan.process(iq, 11, rows=rows, peaks=peaks, avg=avg)
         ctx.sync()
-        del os.environ[var]
+        ctx.set_option("kernel", 0)
         print(var, float(rows.max()))
     fs = 2_400_000
     chain = rfa.ChainPlan(ctx, rfa.FMT_U8, fs, 100_000_000, 100_250_000, rfa.MODE_WFM, 100_000, 8192, 1.0, rfa.SUM_FMA)

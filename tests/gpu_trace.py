@@ -1,7 +1,7 @@
-"""Phase timeline of the single-frame spectrum kernel (RFA_TRACE build, RFA_DUAL=0): cycles per phase."""
+"""Phase timeline of the single-frame spectrum kernel (-DRFA_TRACE build; DUAL=1 in the environment of this script selects the lab build's dual-frame kernel): cycles per phase."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ.setdefault("RFA_DUAL", "0")
+DUAL = os.environ.get("DUAL", "0")
 import numpy as np, torch
 import rfanalyzer_b200 as rfa
 from rfanalyzer_b200 import _lib
@@ -9,6 +9,8 @@ from oracle import oracle as O
 
 N = int(os.environ.get("N", "4096")); F = (1 << 24) // N
 stream = torch.cuda.Stream(); ctx = rfa.Context(0, stream)
+if DUAL != "0":
+    ctx.set_option("kernel", 1)
 plan = rfa.SpectrumPlan(ctx, 0, N, avg_len=8)
 with torch.cuda.stream(stream):
     iq = torch.from_numpy(O.synth_iq(0, N * F)).cuda()
@@ -19,7 +21,7 @@ with torch.cuda.stream(stream):
         plan.process(iqs[i % 6], F, rows=rows[i % 6], peaks=peaks, avg=avg, peaks_accumulate=True)
     stream.synchronize()
 lib = C.CDLL(_lib.LIB_PATH)
-ctas, slots = (296 if os.environ["RFA_DUAL"] == "0" else 148), 128
+ctas, slots = (296 if DUAL == "0" else 148), 128
 buf = np.zeros((ctas, slots), np.int64)
 assert lib.rfa_debug_trace(buf.ctypes.data_as(C.c_void_p), ctas, slots) == 0
 t0 = buf[:, 0].min()

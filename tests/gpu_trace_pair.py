@@ -1,7 +1,6 @@
-"""Segment timeline of the anti-phase pair kernel (RFA_TRACE build, RFA_PAIR=1): cycles per segment and barrier wait."""
+"""Segment timeline of the anti-phase pair kernel (-DRFA_TRACE -DRFA_LAB build, knob kernel=3): cycles per segment and barrier wait."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["RFA_PAIR"] = "1"
 import numpy as np, torch
 import rfanalyzer_b200 as rfa
 from rfanalyzer_b200 import _lib
@@ -9,6 +8,7 @@ from oracle import oracle as O
 
 N = 4096; F = (1 << 24) // N
 stream = torch.cuda.Stream(); ctx = rfa.Context(0, stream)
+ctx.set_option("kernel", 3)
 plan = rfa.SpectrumPlan(ctx, 0, N, avg_len=8)
 with torch.cuda.stream(stream):
     iq = torch.from_numpy(O.synth_iq(0, N * F)).cuda()

@@ -1,0 +1,232 @@
+"""The experimental kernels of librfa_b200_lab.so (`make lab`): dual-frame, 64 x 64, anti-phase pair and lean N = 4096
+kernels, the fused four-step launch, the residue split for integer input.  All of them measured SLOWER than the
+product's defaults; they stay parity-tested here, outside the shipped library.  This directory is
+only collected when RFA_B200_LIB points at the lab build (tests/test_lab_gpu.py runs it in a subprocess)."""
+import os
+
+import numpy as np
+import pytest
+
+from test_spectrum_gpu import DB_TOL, gpu_spectrum, lin_ok
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _lab_knobs(gpu_ctx):
+    yield
+    for k, v in (("kernel", 0), ("fourstep", 1), ("fs_fused", 0), ("fs_ring_kib", 32 << 10), ("cluster", 1)):
+        gpu_ctx.set_option(k, v)
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("n,frames", [(256, 37), (512, 64), (1024, 37), (2048, 36), (4096, 37), (4096, 1), (4096, 600)])
+def test_dual_frame_kernel_vs_oracle(gpu_ctx, oracle, fmt, n, frames):
+    """spectrum2_kernel (two frames per thread, knob kernel=1): same contract, odd and even frame counts,
+    fewer and more frame pairs than CTAs."""
+    gpu_ctx.set_option("kernel", 1)
+    iq = oracle.synth_iq(fmt, n * frames)
+    r, p, a = oracle.spectrum_run(fmt, iq, n, 3)
+    launches = gpu_ctx.launch_count
+    rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
+    assert gpu_ctx.launch_count > launches
+    assert np.abs(rows - r).max() < DB_TOL
+    assert np.abs(peaks - p).max() < DB_TOL
+    assert np.abs(avg - a).max() < DB_TOL
+    assert lin_ok(rows, r)
+    assert np.array_equal(rows.argmax(axis=1), r.argmax(axis=1))
+    assert np.array_equal(peaks, rows.max(axis=0))
+
+
+def test_dual_frame_kernel_ring_and_history(gpu_ctx, oracle):
+    """The reference's backwards ring with more frames than rows, through the dual-frame kernel."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    gpu_ctx.set_option("kernel", 1)
+    n, L, ring = 1024, 5, 300
+    L_o = oracle.lib()
+    proc = L_o.orc_fftproc_new(ring, 1)
+    plan = rfa.SpectrumPlan(gpu_ctx, 1, n, avg_len=L)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
+        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
+        write_index, history, first = 0, 0, 0
+        for call, frames in enumerate((3, 1, 311, 8)):
+            iq = oracle.synth_iq(1, n * frames, first=first)
+            first += n * frames
+            r, _, _ = oracle.spectrum_run(1, iq, n, 0)
+            for k in range(frames):
+                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
+            plan.process(torch.from_numpy(iq).cuda(), frames, rows=d_ring, peaks=d_peaks, avg=d_avg,
+                         row0=write_index, row_step=-1, ring_rows=ring, history_rows=history,
+                         peaks_accumulate=call > 0)
+            gpu_ctx.sync()
+            write_index = (write_index - frames) % ring
+            history = min(ring, history + frames)
+            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
+            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
+            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
+            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
+            avg_ref = np.empty(n, np.float32)
+            L_o.orc_time_average(proc, L, avg_ref)
+            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
+    L_o.orc_fftproc_free(proc)
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_two_pass_64x64_kernel_vs_oracle(gpu_ctx, oracle, fmt):
+    """spectrum64_kernel (knob kernel=2, N = 4096, no time average): 64 points per thread, one exchange."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    gpu_ctx.set_option("kernel", 2)
+    n, frames = 4096, 601
+    iq = oracle.synth_iq(fmt, n * frames)
+    r, p, _ = oracle.spectrum_run(fmt, iq, n, 0)
+    plan = rfa.SpectrumPlan(gpu_ctx, fmt, n, avg_len=0)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        rows = torch.zeros((frames, n), dtype=torch.float32, device="cuda")
+        peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        plan.process(torch.from_numpy(iq).cuda(), frames, rows=rows, peaks=peaks)
+        gpu_ctx.sync()
+    rows, peaks = rows.cpu().numpy(), peaks.cpu().numpy()
+    assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL
+    assert lin_ok(rows, r)
+    assert np.array_equal(peaks, rows.max(axis=0))
+
+
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_fourstep_matches_the_residue_split_kernel(gpu_ctx, oracle, n):
+    """Two factorisations of the same transform: fourstep_kernel.cuh vs spectrum_kernel's residue split
+    (lab knob fourstep=0)."""
+    frames = 6
+    iq = oracle.synth_iq(0, n * frames)
+    rows4, peaks4, avg4 = gpu_spectrum(gpu_ctx, 0, iq, n, L=3)
+    gpu_ctx.set_option("fourstep", 0)
+    gpu_ctx.set_option("cluster", 0)
+    rows1, peaks1, avg1 = gpu_spectrum(gpu_ctx, 0, iq, n, L=3)
+    assert np.abs(rows4 - rows1).max() < DB_TOL
+    assert np.abs(peaks4 - peaks1).max() < DB_TOL
+    assert np.abs(avg4 - avg1).max() < DB_TOL
+    assert np.array_equal(rows4.argmax(axis=1), rows1.argmax(axis=1))
+
+
+@pytest.mark.parametrize("fmt,n,frames", [(0, 65536, 40), (2, 32768, 150)])
+def test_fourstep_fused_producer_consumer_launch(gpu_ctx, oracle, fmt, n, frames):
+    """knob fs_fused=1: both steps in one cooperative launch, Z in a ring that is smaller than the call (the ring
+    hand-over is exercised: fs_ring_kib=1024 keeps only the minimum number of frames).  Identical rows."""
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows_2k, peaks_2k, avg_2k = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
+    gpu_ctx.set_option("fs_fused", 1)
+    gpu_ctx.set_option("cluster", 0)
+    gpu_ctx.set_option("fs_ring_kib", 1024)
+    rows_f, peaks_f, avg_f = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
+    assert np.array_equal(rows_f, rows_2k) and np.array_equal(peaks_f, peaks_2k) and np.array_equal(avg_f, avg_2k)
+
+
+# ---- anti-phase pair kernel (spectrum_pair_kernel.cuh, knob kernel=3), N = 4096 ----
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("frames", [1, 2, 37, 600, 4096])
+def test_pair_kernel_is_identical_to_the_default_kernel(gpu_ctx, oracle, fmt, frames):
+    """Same per-thread phase functions in another schedule (two frames per 512-thread CTA, one segment apart):
+    rows, peaks and the time average must be bit-identical to the default kernel's, for odd and even frame
+    counts, fewer and more frame pairs than SMs."""
+    n = 4096
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows_d, peaks_d, avg_d = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
+    gpu_ctx.set_option("kernel", 3)
+    rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
+    assert np.array_equal(rows, rows_d) and np.array_equal(peaks, peaks_d) and np.array_equal(avg, avg_d)
+    if frames <= 64:
+        r, p, a = oracle.spectrum_run(fmt, iq, n, 8)
+        assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL and np.abs(avg - a).max() < DB_TOL
+
+
+def test_pair_kernel_ring_history_and_repeated_launches(gpu_ctx, oracle):
+    """Backwards ring with more frames than rows, accumulating peaks, average over earlier calls' rows; launched
+    many times in a row (the ticket counters must re-arm)."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    gpu_ctx.set_option("kernel", 3)
+    n, L, ring = 4096, 5, 300
+    L_o = oracle.lib()
+    proc = L_o.orc_fftproc_new(ring, 1)
+    plan = rfa.SpectrumPlan(gpu_ctx, 0, n, avg_len=L)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
+        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
+        write_index, history, first = 0, 0, 0
+        for call, frames in enumerate((3, 1, 311, 8, 2, 2, 2, 75)):
+            iq = oracle.synth_iq(0, n * frames, first=first)
+            first += n * frames
+            r, _, _ = oracle.spectrum_run(0, iq, n, 0)
+            for k in range(frames):
+                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
+            plan.process(torch.from_numpy(iq).cuda(), frames, rows=d_ring, peaks=d_peaks, avg=d_avg,
+                         row0=write_index, row_step=-1, ring_rows=ring, history_rows=history,
+                         peaks_accumulate=call > 0)
+            gpu_ctx.sync()
+            write_index = (write_index - frames) % ring
+            history = min(ring, history + frames)
+            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
+            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
+            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
+            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
+            avg_ref = np.empty(n, np.float32)
+            L_o.orc_time_average(proc, L, avg_ref)
+            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
+    L_o.orc_fftproc_free(proc)
+
+
+# ---- three-CTAs-per-SM kernel (spectrum_lean_kernel.cuh, knob kernel=4), N = 4096, 8-bit IQ ----
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("frames", [1, 2, 37, 600, 4096])
+def test_lean_kernel_is_identical_to_the_default_kernel(gpu_ctx, oracle, fmt, frames):
+    """Window taps from shared memory and last-pass twiddles through L1 instead of registers, one exchange frame,
+    three CTAs per SM: the same operations in the same order, so rows, peaks and average are bit-identical."""
+    n = 4096
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows_d, peaks_d, avg_d = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
+    gpu_ctx.set_option("kernel", 4)
+    rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
+    assert np.array_equal(rows, rows_d) and np.array_equal(peaks, peaks_d) and np.array_equal(avg, avg_d)
+    if frames <= 64:
+        r, p, a = oracle.spectrum_run(fmt, iq, n, 8)
+        assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL and np.abs(avg - a).max() < DB_TOL
+
+
+def test_lean_kernel_ring_history_and_repeated_launches(gpu_ctx, oracle):
+    import torch
+    import rfanalyzer_b200 as rfa
+    gpu_ctx.set_option("kernel", 4)
+    n, L, ring = 4096, 5, 300
+    L_o = oracle.lib()
+    proc = L_o.orc_fftproc_new(ring, 1)
+    plan = rfa.SpectrumPlan(gpu_ctx, 1, n, avg_len=L)
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
+        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
+        write_index, history, first = 0, 0, 0
+        for call, frames in enumerate((3, 1, 311, 8, 2, 2, 2, 75)):
+            iq = oracle.synth_iq(1, n * frames, first=first)
+            first += n * frames
+            r, _, _ = oracle.spectrum_run(1, iq, n, 0)
+            for k in range(frames):
+                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
+            plan.process(torch.from_numpy(iq).cuda(), frames, rows=d_ring, peaks=d_peaks, avg=d_avg,
+                         row0=write_index, row_step=-1, ring_rows=ring, history_rows=history,
+                         peaks_accumulate=call > 0)
+            gpu_ctx.sync()
+            write_index = (write_index - frames) % ring
+            history = min(ring, history + frames)
+            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
+            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
+            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
+            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
+            avg_ref = np.empty(n, np.float32)
+            L_o.orc_time_average(proc, L, avg_ref)
+            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
+    L_o.orc_fftproc_free(proc)
+

@@ -14,6 +14,16 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 DB_TOL = 0.01
 
 
+@pytest.fixture(autouse=True)
+def _default_knobs(request):
+    """Tests may turn the context's knobs (rfa_ctx_set_option); every test starts from the defaults."""
+    yield
+    if "gpu_ctx" in request.fixturenames:
+        ctx = request.getfixturevalue("gpu_ctx")
+        for k, v in (("fs_batch_kib", 128 << 10), ("fs_tma", 1), ("fs_ztma", 1), ("staged", 1), ("pdl", 1), ("cluster", 1)):
+            ctx.set_option(k, v)
+
+
 def lin_ok(rows, ref):
     lin, lin_ref = 10.0 ** (rows.astype(np.float64) / 5.0), 10.0 ** (ref.astype(np.float64) / 5.0)
     floor = 1e-6 * lin_ref.max(axis=-1, keepdims=True)
@@ -239,82 +249,6 @@ def test_full_size_properties(gpu_ctx, oracle):
         assert np.abs(rows[f].cpu().numpy() - r[0]).max() < DB_TOL
 
 
-@pytest.mark.parametrize("fmt", [0, 1, 2])
-@pytest.mark.parametrize("n,frames", [(256, 37), (512, 64), (1024, 37), (2048, 36), (4096, 37), (4096, 1), (4096, 600)])
-def test_dual_frame_kernel_vs_oracle(gpu_ctx, oracle, monkeypatch, fmt, n, frames):
-    """spectrum2_kernel (two frames per thread, RFA_DUAL=1): same contract, odd and even frame counts,
-    fewer and more frame pairs than CTAs."""
-    monkeypatch.setenv("RFA_DUAL", "1")
-    iq = oracle.synth_iq(fmt, n * frames)
-    r, p, a = oracle.spectrum_run(fmt, iq, n, 3)
-    launches = gpu_ctx.launch_count
-    rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
-    assert gpu_ctx.launch_count > launches
-    assert np.abs(rows - r).max() < DB_TOL
-    assert np.abs(peaks - p).max() < DB_TOL
-    assert np.abs(avg - a).max() < DB_TOL
-    assert lin_ok(rows, r)
-    assert np.array_equal(rows.argmax(axis=1), r.argmax(axis=1))
-    assert np.array_equal(peaks, rows.max(axis=0))
-
-
-def test_dual_frame_kernel_ring_and_history(gpu_ctx, oracle, monkeypatch):
-    """The reference's backwards ring with more frames than rows, through the dual-frame kernel."""
-    import torch
-    import rfanalyzer_b200 as rfa
-    monkeypatch.setenv("RFA_DUAL", "1")
-    n, L, ring = 1024, 5, 300
-    L_o = oracle.lib()
-    proc = L_o.orc_fftproc_new(ring, 1)
-    plan = rfa.SpectrumPlan(gpu_ctx, 1, n, avg_len=L)
-    with torch.cuda.stream(gpu_ctx.torch_stream):
-        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
-        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
-        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
-        write_index, history, first = 0, 0, 0
-        for call, frames in enumerate((3, 1, 311, 8)):
-            iq = oracle.synth_iq(1, n * frames, first=first)
-            first += n * frames
-            r, _, _ = oracle.spectrum_run(1, iq, n, 0)
-            for k in range(frames):
-                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
-            plan.process(torch.from_numpy(iq).cuda(), frames, rows=d_ring, peaks=d_peaks, avg=d_avg,
-                         row0=write_index, row_step=-1, ring_rows=ring, history_rows=history,
-                         peaks_accumulate=call > 0)
-            gpu_ctx.sync()
-            write_index = (write_index - frames) % ring
-            history = min(ring, history + frames)
-            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
-            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
-            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
-            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
-            avg_ref = np.empty(n, np.float32)
-            L_o.orc_time_average(proc, L, avg_ref)
-            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
-    L_o.orc_fftproc_free(proc)
-
-
-@pytest.mark.parametrize("fmt", [0, 1, 2])
-def test_two_pass_64x64_kernel_vs_oracle(gpu_ctx, oracle, monkeypatch, fmt):
-    """spectrum64_kernel (RFA_K64=1, N = 4096, no time average): 64 points per thread, one exchange."""
-    import torch
-    import rfanalyzer_b200 as rfa
-    monkeypatch.setenv("RFA_K64", "1")
-    n, frames = 4096, 601
-    iq = oracle.synth_iq(fmt, n * frames)
-    r, p, _ = oracle.spectrum_run(fmt, iq, n, 0)
-    plan = rfa.SpectrumPlan(gpu_ctx, fmt, n, avg_len=0)
-    with torch.cuda.stream(gpu_ctx.torch_stream):
-        rows = torch.zeros((frames, n), dtype=torch.float32, device="cuda")
-        peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
-        plan.process(torch.from_numpy(iq).cuda(), frames, rows=rows, peaks=peaks)
-        gpu_ctx.sync()
-    rows, peaks = rows.cpu().numpy(), peaks.cpu().numpy()
-    assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL
-    assert lin_ok(rows, r)
-    assert np.array_equal(peaks, rows.max(axis=0))
-
-
 @pytest.mark.parametrize("fmt,n,frames,first,count,chunk", [(0, 4096, 300, 0, -1, 64), (1, 1024, 1000, 17, 900, 0),
                                                             (2, 2048, 123, 3, -1, 50), (0, 4096, 5, 0, -1, 2)])
 def test_process_file_matches_the_in_memory_pass(gpu_ctx, oracle, tmp_path, fmt, n, frames, first, count, chunk):
@@ -347,13 +281,13 @@ def parse_name(ctx, path):
 # ---- four-step path (fourstep_kernel.cuh), N = 32768 / 65536 ----
 @pytest.mark.parametrize("fmt,n,frames,batch_kib", [(0, 65536, 7, 1024), (2, 32768, 9, 512), (1, 65536, 3, 0)])
 def test_fourstep_batches_ring_and_history(gpu_ctx, oracle, monkeypatch, fmt, n, frames, batch_kib):
-    """Several batches through a small intermediate buffer (RFA_FS_BATCH_KIB, read per call), rows into a
+    """Several batches through a small intermediate buffer (knob "fs_batch_kib"), rows into a
     backwards ring with history, accumulating peaks, average over ring rows."""
     import torch
     import rfanalyzer_b200 as rfa
     L, ring = 4, 12
-    if batch_kib:
-        monkeypatch.setenv("RFA_FS_BATCH_KIB", str(batch_kib))
+    if batch_kib:   # several batches through a small intermediate buffer (context knob, restored by the fixture below)
+        gpu_ctx.set_option("fs_batch_kib", batch_kib)
     plan = rfa.SpectrumPlan(gpu_ctx, fmt, n, avg_len=L)
     L_o = oracle.lib()
     proc = L_o.orc_fftproc_new(ring, 1)
@@ -383,37 +317,20 @@ def test_fourstep_batches_ring_and_history(gpu_ctx, oracle, monkeypatch, fmt, n,
     L_o.orc_fftproc_free(proc)
 
 
-@pytest.mark.parametrize("n", [32768, 65536])
-def test_fourstep_matches_the_residue_split_kernel(gpu_ctx, oracle, monkeypatch, n):
-    """Two factorisations of the same transform: fourstep_kernel.cuh vs spectrum_kernel's residue split
-    (RFA_FOURSTEP=0, read per call)."""
-    frames = 6
-    iq = oracle.synth_iq(0, n * frames)
-    rows4, peaks4, avg4 = gpu_spectrum(gpu_ctx, 0, iq, n, L=3)
-    monkeypatch.setenv("RFA_FOURSTEP", "0")
-    rows1, peaks1, avg1 = gpu_spectrum(gpu_ctx, 0, iq, n, L=3)
-    assert np.abs(rows4 - rows1).max() < DB_TOL
-    assert np.abs(peaks4 - peaks1).max() < DB_TOL
-    assert np.abs(avg4 - avg1).max() < DB_TOL
-    assert np.array_equal(rows4.argmax(axis=1), rows1.argmax(axis=1))
-
-
 @pytest.mark.parametrize("fmt,n", [(0, 65536), (1, 32768), (2, 65536), (2, 32768)])
 def test_fourstep_tensor_map_staging_equals_per_thread_loads(gpu_ctx, oracle, monkeypatch, fmt, n):
     """The column kernel reads its raw IQ either through a 2-D tensor-map box per frame (default, 16-byte aligned
-    input) or with per-thread loads (RFA_FS_TMA=0, and any misaligned input): same arithmetic, identical rows."""
+    input) or with per-thread loads (knob "fs_tma" = 0, and any misaligned input): same arithmetic, identical rows."""
     import torch
     import rfanalyzer_b200 as rfa
     frames = 5
     iq = oracle.synth_iq(fmt, n * frames)
     rows_t, peaks_t, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
-    monkeypatch.setenv("RFA_FS_TMA", "0")
-    rows_l, peaks_l, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
-    monkeypatch.delenv("RFA_FS_TMA")
+    with gpu_ctx.options(fs_tma=0):
+        rows_l, peaks_l, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
     assert np.array_equal(rows_t, rows_l) and np.array_equal(peaks_t, peaks_l)
-    monkeypatch.setenv("RFA_FS_ZTMA", "0")   # tensor-map loads, per-thread stores of the intermediate
-    rows_s, peaks_s, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
-    monkeypatch.delenv("RFA_FS_ZTMA")
+    with gpu_ctx.options(fs_ztma=0):   # tensor-map loads, per-thread stores of the intermediate
+        rows_s, peaks_s, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
     assert np.array_equal(rows_t, rows_s) and np.array_equal(peaks_t, peaks_s)
     # an input that starts 4 bytes into an allocation is not 16-byte aligned: the launcher must fall back by itself
     plan = rfa.SpectrumPlan(gpu_ctx, fmt, n)
@@ -424,125 +341,6 @@ def test_fourstep_tensor_map_staging_equals_per_thread_loads(gpu_ctx, oracle, mo
         plan.process(buf[4:], frames, rows=rows_m)
         gpu_ctx.sync()
     assert np.array_equal(rows_m.cpu().numpy(), rows_t)
-
-
-@pytest.mark.parametrize("fmt,n,frames", [(0, 65536, 40), (2, 32768, 150)])
-def test_fourstep_fused_producer_consumer_launch(gpu_ctx, oracle, monkeypatch, fmt, n, frames):
-    """RFA_FS_FUSED=1: both steps in one cooperative launch, Z in a ring that is smaller than the call (the ring
-    hand-over is exercised: RFA_FS_RING_KIB=1024 keeps only the minimum number of frames).  Identical rows."""
-    iq = oracle.synth_iq(fmt, n * frames)
-    rows_2k, peaks_2k, avg_2k = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
-    monkeypatch.setenv("RFA_FS_FUSED", "1")
-    monkeypatch.setenv("RFA_FS_RING_KIB", "1024")
-    rows_f, peaks_f, avg_f = gpu_spectrum(gpu_ctx, fmt, iq, n, L=3)
-    assert np.array_equal(rows_f, rows_2k) and np.array_equal(peaks_f, peaks_2k) and np.array_equal(avg_f, avg_2k)
-
-
-# ---- anti-phase pair kernel (spectrum_pair_kernel.cuh, RFA_PAIR=1), N = 4096 ----
-@pytest.mark.parametrize("fmt", [0, 1, 2])
-@pytest.mark.parametrize("frames", [1, 2, 37, 600, 4096])
-def test_pair_kernel_is_identical_to_the_default_kernel(gpu_ctx, oracle, monkeypatch, fmt, frames):
-    """Same per-thread phase functions in another schedule (two frames per 512-thread CTA, one segment apart):
-    rows, peaks and the time average must be bit-identical to the default kernel's, for odd and even frame
-    counts, fewer and more frame pairs than SMs."""
-    n = 4096
-    iq = oracle.synth_iq(fmt, n * frames)
-    rows_d, peaks_d, avg_d = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
-    monkeypatch.setenv("RFA_PAIR", "1")
-    rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
-    assert np.array_equal(rows, rows_d) and np.array_equal(peaks, peaks_d) and np.array_equal(avg, avg_d)
-    if frames <= 64:
-        r, p, a = oracle.spectrum_run(fmt, iq, n, 8)
-        assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL and np.abs(avg - a).max() < DB_TOL
-
-
-def test_pair_kernel_ring_history_and_repeated_launches(gpu_ctx, oracle, monkeypatch):
-    """Backwards ring with more frames than rows, accumulating peaks, average over earlier calls' rows; launched
-    many times in a row (the ticket counters must re-arm)."""
-    import torch
-    import rfanalyzer_b200 as rfa
-    monkeypatch.setenv("RFA_PAIR", "1")
-    n, L, ring = 4096, 5, 300
-    L_o = oracle.lib()
-    proc = L_o.orc_fftproc_new(ring, 1)
-    plan = rfa.SpectrumPlan(gpu_ctx, 0, n, avg_len=L)
-    with torch.cuda.stream(gpu_ctx.torch_stream):
-        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
-        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
-        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
-        write_index, history, first = 0, 0, 0
-        for call, frames in enumerate((3, 1, 311, 8, 2, 2, 2, 75)):
-            iq = oracle.synth_iq(0, n * frames, first=first)
-            first += n * frames
-            r, _, _ = oracle.spectrum_run(0, iq, n, 0)
-            for k in range(frames):
-                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
-            plan.process(torch.from_numpy(iq).cuda(), frames, rows=d_ring, peaks=d_peaks, avg=d_avg,
-                         row0=write_index, row_step=-1, ring_rows=ring, history_rows=history,
-                         peaks_accumulate=call > 0)
-            gpu_ctx.sync()
-            write_index = (write_index - frames) % ring
-            history = min(ring, history + frames)
-            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
-            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
-            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
-            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
-            avg_ref = np.empty(n, np.float32)
-            L_o.orc_time_average(proc, L, avg_ref)
-            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
-    L_o.orc_fftproc_free(proc)
-
-
-# ---- three-CTAs-per-SM kernel (spectrum_lean_kernel.cuh, RFA_LEAN=1), N = 4096, 8-bit IQ ----
-@pytest.mark.parametrize("fmt", [0, 1])
-@pytest.mark.parametrize("frames", [1, 2, 37, 600, 4096])
-def test_lean_kernel_is_identical_to_the_default_kernel(gpu_ctx, oracle, monkeypatch, fmt, frames):
-    """Window taps from shared memory and last-pass twiddles through L1 instead of registers, one exchange frame,
-    three CTAs per SM: the same operations in the same order, so rows, peaks and average are bit-identical."""
-    n = 4096
-    iq = oracle.synth_iq(fmt, n * frames)
-    rows_d, peaks_d, avg_d = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
-    monkeypatch.setenv("RFA_LEAN", "1")
-    rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
-    assert np.array_equal(rows, rows_d) and np.array_equal(peaks, peaks_d) and np.array_equal(avg, avg_d)
-    if frames <= 64:
-        r, p, a = oracle.spectrum_run(fmt, iq, n, 8)
-        assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL and np.abs(avg - a).max() < DB_TOL
-
-
-def test_lean_kernel_ring_history_and_repeated_launches(gpu_ctx, oracle, monkeypatch):
-    import torch
-    import rfanalyzer_b200 as rfa
-    monkeypatch.setenv("RFA_LEAN", "1")
-    n, L, ring = 4096, 5, 300
-    L_o = oracle.lib()
-    proc = L_o.orc_fftproc_new(ring, 1)
-    plan = rfa.SpectrumPlan(gpu_ctx, 1, n, avg_len=L)
-    with torch.cuda.stream(gpu_ctx.torch_stream):
-        d_ring = torch.full((ring, n), -9999.0, dtype=torch.float32, device="cuda")
-        d_peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
-        d_avg = torch.zeros(n, dtype=torch.float32, device="cuda")
-        write_index, history, first = 0, 0, 0
-        for call, frames in enumerate((3, 1, 311, 8, 2, 2, 2, 75)):
-            iq = oracle.synth_iq(1, n * frames, first=first)
-            first += n * frames
-            r, _, _ = oracle.spectrum_run(1, iq, n, 0)
-            for k in range(frames):
-                L_o.orc_fftproc_push(proc, np.ascontiguousarray(r[k]), n, 100_000_000, 20_000_000)
-            plan.process(torch.from_numpy(iq).cuda(), frames, rows=d_ring, peaks=d_peaks, avg=d_avg,
-                         row0=write_index, row_step=-1, ring_rows=ring, history_rows=history,
-                         peaks_accumulate=call > 0)
-            gpu_ctx.sync()
-            write_index = (write_index - frames) % ring
-            history = min(ring, history + frames)
-            ring_ref = np.stack([np.ctypeslib.as_array(L_o.orc_fftproc_row(proc, i), shape=(n,)) for i in range(ring)])
-            assert np.abs(d_ring.cpu().numpy() - ring_ref).max() < DB_TOL
-            peaks_ref = np.ctypeslib.as_array(L_o.orc_fftproc_peaks(proc), shape=(n,))
-            assert np.abs(d_peaks.cpu().numpy() - peaks_ref).max() < DB_TOL
-            avg_ref = np.empty(n, np.float32)
-            L_o.orc_time_average(proc, L, avg_ref)
-            assert np.abs(d_avg.cpu().numpy() - avg_ref).max() < DB_TOL
-    L_o.orc_fftproc_free(proc)
 
 
 @pytest.mark.parametrize("n", [32768, 65536])
