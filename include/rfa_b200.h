@@ -116,12 +116,22 @@ int rfa_windowed_fft_logmag(rfa_ctx *ctx, const float *re, const float *im, floa
  * Scheduler.kt:266 (fill) + NativeDsp.kt:43-62 + nativedsp.cpp:44-81 +
  * FftProcessor.kt:224-245 (row store, peak hold) + AnalyzerSurface.kt:710-714 (time average)
  * in one pass over the IQ bytes. */
+/* How `avg` is formed.  BOXCAR is the reference (AnalyzerSurface.kt:710-714: mean of the newest avg_len+1 rows) and
+ * the default.  EMA is an extra option the reference does not have: a_k = a_(k-1) + alpha*(row_k - a_(k-1)) over the
+ * frames in time order, float32, each operation rounded (no FMA); the first frame starts it (a_0 = row_0) unless
+ * rfa_spectrum_out.avg_accumulate continues from the value already in `avg`.  The kernel walks only as many of the
+ * newest frames as carry weight above 2^-40 (and are still stored), so the result equals the full recurrence to
+ * far below one float32 ulp; a run of -inf rows (all-zero frames) poisons the average exactly as the recurrence says. */
+enum { RFA_AVG_BOXCAR = 0, RFA_AVG_EMA = 1 };
+
 typedef struct {
     int format;    /* RFA_FMT_* */
     int fft_size;  /* power of two, 16 .. 65536 (the app offers 1024 .. 65536, DisplayTab.kt:108-111) */
     int window;    /* RFA_WIN_* */
     int avg_len;   /* L = fftAverageLength, 0 .. 30: the average spans the newest L+1 rows */
     int peak_hold; /* FftProcessor.fftPeakHold */
+    int avg_mode;  /* RFA_AVG_BOXCAR (0, the reference) or RFA_AVG_EMA */
+    float ema_alpha; /* RFA_AVG_EMA: weight of the newest row, 0 < alpha <= 1 */
 } rfa_spectrum_desc;
 
 typedef struct {
@@ -133,7 +143,8 @@ typedef struct {
     long long history_rows; /* ring only: rows already valid before this call (for avg)      */
     float *peaks;         /* [n] running element-wise max of all rows, or NULL               */
     int peaks_accumulate; /* 1: continue from the values in `peaks`; 0: restart at -999999f  */
-    float *avg;           /* [n] mean of the newest avg_len+1 rows, or NULL                  */
+    float *avg;           /* [n] mean of the newest avg_len+1 rows (or the EMA), or NULL      */
+    int avg_accumulate;   /* RFA_AVG_EMA: 1 = continue from the values in `avg`              */
 } rfa_spectrum_out;
 
 int rfa_spectrum_plan_create(rfa_ctx *ctx, const rfa_spectrum_desc *desc, rfa_spectrum_plan **out);
@@ -151,6 +162,12 @@ long long rfa_spectrum_algorithmic_bytes(const rfa_spectrum_plan *plan, long lon
 int rfa_average_rows(rfa_ctx *ctx, const float *rows, long long newest, long long dir, long long ring_rows,
                      long long row_stride, long long valid, int avg_len, int n, float *avg, int mem_rows,
                      int mem_avg);
+/* RFA_AVG_EMA over frames first .. last (inclusive, time order) of device rows laid out as in rfa_spectrum_out
+ * (row of frame f = (row0 + f*row_step) mod ring_rows); from_state: continue from `avg` instead of starting at
+ * the first row.  avg per mem_avg. */
+int rfa_ema_rows(rfa_ctx *ctx, const float *rows, long long row0, long long row_step, long long ring_rows,
+                 long long row_stride, long long first, long long last, float alpha, int from_state, int n,
+                 float *avg, int mem_avg);
 /* FftProcessor.kt:143-157: host helper for the channel's bin range ... */
 int rfa_channel_bins(int n, long long frequency, int sample_rate, long long chan_start, long long chan_end,
                      int *bin_start, int *bin_end);

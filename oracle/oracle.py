@@ -71,6 +71,7 @@ def _declare(L):
         "orc_signal_strength": (C.c_int, [_f32p, C.c_int, C.c_longlong, C.c_int, C.c_longlong, C.c_longlong,
                                           C.POINTER(C.c_float)]),
         "orc_time_average": (None, [vp, C.c_int, _f32p]),
+        "orc_ema_rows": (None, [_f32p, C.c_longlong, C.c_int, C.c_float, C.c_void_p, _f32p]),
         "orc_draw_preprocess": (None, [vp, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_float, C.c_float,
                                        C.c_int, C.c_int, _f32p, _i32p, C.c_void_p]),
         "orc_window_value": (C.c_float, [C.c_int, C.c_double, C.c_int, C.c_int]),
@@ -288,6 +289,15 @@ def spectrum_run(fmt, iq, N, L=0):
     avg = np.empty(N, dtype=np.float32)
     lib().orc_spectrum_run(fmt, iq, ns, N, L, _vp(rows), _vp(peaks), _vp(avg))
     return rows, peaks, avg
+
+
+def ema_rows(rows, alpha, init=None):
+    """Exponential average of rows[F][N] in time order (orc_ema_rows; not in the reference)."""
+    rows = np.ascontiguousarray(rows, np.float32)
+    avg = np.empty(rows.shape[1], np.float32)
+    init = None if init is None else np.ascontiguousarray(init, np.float32)
+    lib().orc_ema_rows(rows, rows.shape[0], rows.shape[1], float(alpha), _vp(init), avg)
+    return avg
 
 
 def ref_spectrum_run(fmt, iq, N, L=0, nthreads=1, want_rows=True):

@@ -520,6 +520,27 @@ void orc_time_average(const orc_fftproc *p, int L, float *avg) {
     for (int i = 0; i < N; i++) avg[i] = avg[i] / (L + 1);
 }
 
+void orc_ema_rows(const float *rows, long long frames, int N, float alpha, const float *init, float *avg) {
+    /* not in the reference (AnalyzerSurface.kt:710-714 is a box-car mean): the sequential definition of the
+     * north-star's exponential-averaging option, compiled without FMA contraction like everything here */
+    for (int i = 0; i < N; i++) {
+        long long f = 0;
+        float a;
+        if (init) {
+            a = init[i];
+        } else {
+            a = rows[i];
+            f = 1;
+        }
+        for (; f < frames; f++) {
+            float d = rows[(size_t)f * N + i] - a;
+            float t = alpha * d;
+            a = a + t;
+        }
+        avg[i] = a;
+    }
+}
+
 void orc_draw_preprocess(const orc_fftproc *p, int width, int fftHeight,
                          long long viewportFrequency, long long viewportSampleRate,
                          float minDB, float maxDB, int L, int colorMapSize,

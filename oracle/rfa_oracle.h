@@ -95,6 +95,10 @@ int orc_signal_strength(const float *mag, int N, long long frequency, int sample
 /* AnalyzerSurface.kt:710-714 for the 1 bin == 1 pixel case: mean of newest L+1 rows,
  * summed newest->oldest in float32 */
 void orc_time_average(const orc_fftproc *p, int L, float *avg);
+/* Exponential average of `frames` rows (time order), an option the REFERENCE DOES NOT HAVE (its average is the
+ * box-car above); this is the definition the GPU option RFA_AVG_EMA is held to: a = a + alpha*(row - a), float32,
+ * every operation rounded; init == NULL starts at the first row. */
+void orc_ema_rows(const float *rows, long long frames, int N, float alpha, const float *init, float *avg);
 /* AnalyzerSurface.kt:599-743 arithmetic (per-pixel mean, time average, colour index) */
 void orc_draw_preprocess(const orc_fftproc *p, int width, int fftHeight,
                          long long viewportFrequency, long long viewportSampleRate,

@@ -7,7 +7,7 @@ This package is the host-side mirror of the reference classes that sit on that p
 Demodulator, AudioSink) plus thin batch objects (Context, SpectrumPlan, ChainPlan).
 """
 from . import _lib
-from ._lib import (FMT_S8, FMT_U8, FMT_S16LE, WIN_BLACKMAN_REF, WIN_HANN, WIN_RECT, MEM_HOST, MEM_DEVICE,
+from ._lib import (FMT_S8, FMT_U8, FMT_S16LE, WIN_BLACKMAN_REF, WIN_HANN, WIN_RECT, MEM_HOST, MEM_DEVICE, AVG_BOXCAR, AVG_EMA,
                    MODE_OFF, MODE_AM, MODE_NFM, MODE_WFM, MODE_LSB, MODE_USB, MODE_CW, SUM_FMA, SUM_EXACT,
                    BYTES_PER_SAMPLE, RfaError)
 from .engine import Context, SpectrumPlan, synth_iq, synth_step, default_synth_components

@@ -17,6 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = range(5)
 MEM_HOST, MEM_DEVICE = 0, 1
 FMT_S8, FMT_U8, FMT_S16LE = 0, 1, 2
 WIN_BLACKMAN_REF, WIN_HANN, WIN_RECT = 0, 1, 2
+AVG_BOXCAR, AVG_EMA = 0, 1
 TAPWIN_BLACKMAN, TAPWIN_HAMMING, TAPWIN_KAISER = 0, 1, 2
 MODE_OFF, MODE_AM, MODE_NFM, MODE_WFM, MODE_LSB, MODE_USB, MODE_CW = range(7)
 SUM_FMA, SUM_EXACT = 0, 1
@@ -31,13 +32,14 @@ class RfaError(RuntimeError):
 
 class SpectrumDesc(C.Structure):
     _fields_ = [("format", C.c_int), ("fft_size", C.c_int), ("window", C.c_int), ("avg_len", C.c_int),
-                ("peak_hold", C.c_int)]
+                ("peak_hold", C.c_int), ("avg_mode", C.c_int), ("ema_alpha", C.c_float)]
 
 
 class SpectrumOut(C.Structure):
     _fields_ = [("rows", C.c_void_p), ("row0", C.c_longlong), ("row_step", C.c_longlong),
                 ("ring_rows", C.c_longlong), ("row_stride", C.c_longlong), ("history_rows", C.c_longlong),
-                ("peaks", C.c_void_p), ("peaks_accumulate", C.c_int), ("avg", C.c_void_p)]
+                ("peaks", C.c_void_p), ("peaks_accumulate", C.c_int), ("avg", C.c_void_p),
+                ("avg_accumulate", C.c_int)]
 
 
 class RecordingInfo(C.Structure):
@@ -107,6 +109,7 @@ SIGNATURES = {
     "rfa_spectrum_process": (_i, [_vp, _vp, _ll, C.POINTER(SpectrumOut), _i]),
     "rfa_spectrum_algorithmic_bytes": (_ll, [_vp, _ll, _i]),
     "rfa_average_rows": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _vp, _i, _i]),
+    "rfa_ema_rows": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _ll, _f, _i, _i, _vp, _i]),
     "rfa_channel_bins": (_i, [_i, _ll, _i, _ll, _ll, _pi, _pi]),
     "rfa_channel_strength": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _vp, _i]),
     "rfa_shift_rows": (_i, [_vp, _vp, _ll, _ll, _i, _i]),

@@ -419,6 +419,7 @@ int rfa_windowed_fft_logmag(rfa_ctx *c, const float *re, const float *im, float 
 struct rfa_spectrum_plan {
     rfa_ctx *ctx;
     rfa_spectrum_desc d;
+    long long ema_frames = 0;  // RFA_AVG_EMA: newest frames whose weight (1-alpha)^k is above 2^-40
     const cf *tw = nullptr, *twN = nullptr;
     const float *win = nullptr;
     Buf ticket;     // finished-tail-row counters of the fused kernel
@@ -434,6 +435,7 @@ struct rfa_spectrum_plan {
 struct AvgReq {
     float *avg = nullptr;
     long long valid = 0;
+    bool accumulate = false;  // RFA_AVG_EMA: continue from the values in avg
 };
 
 // one device-resident batch = ONE kernel launch (plus a fill when the peaks restart).
@@ -462,8 +464,9 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
     L.p.nframes = nframes;
     L.p.store_from = store_from;
     L.p.inv_n2 = -3.0102999566398120f * log2f((float)n);  // dB bias, see logmag_db
+    const bool ema = pl->d.avg_mode == RFA_AVG_EMA && aq.avg != nullptr;
     L.p.peaks = peaks;
-    L.p.avg = aq.avg;
+    L.p.avg = ema ? nullptr : aq.avg;  // the exponential average is a row pass of its own after the transform
     L.p.avg_newest = row0 + (nframes - 1) * row_step;
     L.p.avg_dir = -row_step;
     L.p.avg_valid = aq.valid;
@@ -495,16 +498,26 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
         cudaError_t e4 = fourstep_launch(L, fs);
         if (e4 != cudaSuccess) return cuda_fail(e4, "four-step spectrum kernels");
         c->launches += fourstep_launches(n, nframes, fs.z_bytes);
-        if (aq.avg) {
+        if (aq.avg && !ema) {
             average_rows(rows, L.p.avg_newest, L.p.avg_dir, ring_rows, row_stride, aq.valid, pl->d.avg_len, n, aq.avg, c->stream);
             RFA_CK(cudaGetLastError());
             c->launches++;
         }
-        return RFA_OK;
+    } else {
+        cudaError_t e = spectrum_launch(L);
+        if (e != cudaSuccess) return cuda_fail(e, "spectrum kernel");
+        c->launches++;
     }
-    cudaError_t e = spectrum_launch(L);
-    if (e != cudaSuccess) return cuda_fail(e, "spectrum kernel");
-    c->launches++;
+    if (ema) {
+        // frames of this call that are stored and still carry weight, oldest first
+        long long first = nframes - pl->ema_frames;
+        if (first < store_from) first = store_from;
+        if (first < 0) first = 0;
+        ema_rows(rows, row0, row_step, ring_rows, row_stride, first, nframes - 1, pl->d.ema_alpha,
+                 aq.accumulate && first == 0, n, aq.avg, c->stream);
+        RFA_CK(cudaGetLastError());
+        c->launches++;
+    }
     return RFA_OK;
 }
 
@@ -518,10 +531,18 @@ int rfa_spectrum_plan_create(rfa_ctx *c, const rfa_spectrum_desc *d, rfa_spectru
                 "FFT size %d unsupported: need a power of two in 16..65536", d->fft_size);
     RFA_REQUIRE(d->window >= RFA_WIN_BLACKMAN_REF && d->window <= RFA_WIN_RECT, "unknown window %d", d->window);
     RFA_REQUIRE(d->avg_len >= 0 && d->avg_len <= 30, "avg_len %d outside 0..30 (DisplayTab.kt:202-212)", d->avg_len);
+    RFA_REQUIRE(d->avg_mode == RFA_AVG_BOXCAR || d->avg_mode == RFA_AVG_EMA, "unknown averaging mode %d", d->avg_mode);
+    RFA_REQUIRE(d->avg_mode != RFA_AVG_EMA || (d->ema_alpha > 0.0f && d->ema_alpha <= 1.0f),
+                "ema_alpha %g outside (0, 1]", (double)d->ema_alpha);
     if (int rc = c->use()) return rc;
     rfa_spectrum_plan *pl = new rfa_spectrum_plan();
     pl->ctx = c;
     pl->d = *d;
+    if (d->avg_mode == RFA_AVG_EMA) {
+        // (1-alpha)^K < 2^-40: older frames cannot move a float32 result
+        const double keep = 1.0 - (double)d->ema_alpha;
+        pl->ema_frames = keep <= 0.0 ? 1 : (long long)ceil(40.0 * log(2.0) / -log(keep)) + 1;
+    }
     const int n = d->fft_size, nl = n > 16384 ? 16384 : n;
     int rc = c->get_twiddles(nl, &pl->tw);
     if (!rc && (n > 16384 || n == 4096)) rc = c->get_twiddles(-n, &pl->twN);  // 4096: the 64 x 64 kernel's table
@@ -585,6 +606,7 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
     const bool want_peaks = o->peaks != nullptr && pl->d.peak_hold;
     const bool want_avg = o->avg != nullptr;
 
+    const bool ema = pl->d.avg_mode == RFA_AVG_EMA;
     if (mem == RFA_MEM_DEVICE) {
         RFA_REQUIRE(((uintptr_t)iq % (bps == 4 ? 4 : 2)) == 0, "iq pointer misaligned for its format");
         float *rows = o->rows;
@@ -592,14 +614,30 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
         long long store_from = 0;
         if (!rows) {
             if (!want_avg && !want_peaks) return RFA_OK;  // nothing observable is requested
-            // keep just the newest L+1 rows for the time average
-            if (int rc = pl->tail.ensure((size_t)(L + 1) * n * sizeof(float))) return rc;
+            // keep just the rows the average needs: the newest L+1, or the exponential average's window
+            long long keep = L + 1;
+            if (ema && want_avg) {
+                const long long cap = (256LL << 20) / ((long long)n * (long long)sizeof(float));  // at most 256 MiB of rows
+                keep = pl->ema_frames < nframes ? pl->ema_frames : nframes;
+                if (keep > cap && cap >= 1) {
+                    // a window longer than the scratch ring: walk the call in pieces, the average carried between them
+                    rfa_spectrum_out piece = *o;
+                    for (long long f0 = 0; f0 < nframes; f0 += cap) {
+                        const long long nf = nframes - f0 < cap ? nframes - f0 : cap;
+                        piece.peaks_accumulate = o->peaks_accumulate || f0 > 0;
+                        piece.avg_accumulate = o->avg_accumulate || f0 > 0;
+                        if (int rc = rfa_spectrum_process(pl, (const char *)iq + (size_t)f0 * n * bps, nf, &piece, mem)) return rc;
+                    }
+                    return RFA_OK;
+                }
+            }
+            if (int rc = pl->tail.ensure((size_t)keep * n * sizeof(float))) return rc;
             rows = pl->tail.as<float>();
             row0 = 0;
             step = 1;
-            ring = L + 1;
+            ring = keep;
             stride = n;
-            store_from = want_avg ? nframes - (L + 1) : nframes;
+            store_from = want_avg ? nframes - keep : nframes;
         }
         // more frames than ring rows: the older ones would be overwritten by newer frames of this
         // very call (FftProcessor.kt:224-229 runs sequentially), so only the newest ring_rows
@@ -609,6 +647,7 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
         if (want_avg) {
             aq.avg = o->avg;
             aq.valid = nframes;
+            aq.accumulate = o->avg_accumulate != 0;
             if (o->rows && o->ring_rows > 0) {
                 aq.valid = o->history_rows + nframes;
                 if (aq.valid > o->ring_rows) aq.valid = o->ring_rows;
@@ -635,6 +674,11 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
         if (int rc = pl->din[b].ensure(max_chunk * frame_in)) return rc;
         if (store_rows || want_avg)
             if (int rc = pl->drows[b].ensure(max_chunk * frame_out)) return rc;
+    }
+    if (want_avg) {
+        if (int rc = pl->davg.ensure(frame_out)) return rc;
+        if (ema && o->avg_accumulate)
+            RFA_CK(cudaMemcpyAsync(pl->davg.p, o->avg, frame_out, cudaMemcpyHostToDevice, c->stream));
     }
     float *dpeaks = nullptr;
     if (want_peaks) {
@@ -668,14 +712,14 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
         RFA_CK(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
         RFA_CK(cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));  // drows[b] has been copied out
         float *drows = (store_rows || want_avg) ? pl->drows[b].as<float>() : nullptr;
-        long long store_from = store_rows ? 0 : (want_avg && i == nchunks - 1 ? frames - (L + 1) : frames);
+        long long store_from = store_rows || (ema && want_avg) ? 0 : (want_avg && i == nchunks - 1 ? frames - (L + 1) : frames);
         if (drows || dpeaks) {
             float *rows_arg = drows ? drows : pl->din[b].as<float>();  // never written when store_from == frames
             AvgReq aq;
-            if (want_avg && i == nchunks - 1) {
-                if (int rc = pl->davg.ensure(frame_out)) return rc;
+            if (want_avg && (ema || i == nchunks - 1)) {  // the exponential average walks every chunk, carried in davg
                 aq.avg = pl->davg.as<float>();
                 aq.valid = nframes < frames ? nframes : frames;
+                aq.accumulate = o->avg_accumulate != 0 || i > 0;
             }
             if (int rc = spectrum_device(pl, pl->din[b].p, frames, rows_arg, 0, 1, 0, n, store_from, dpeaks,
                                          o->peaks_accumulate != 0 || i > 0, aq))
@@ -717,6 +761,28 @@ int rfa_average_rows(rfa_ctx *c, const float *rows, long long newest, long long 
         davg = c->stage[4].as<float>();
     }
     average_rows(rows, newest, dir, ring_rows, row_stride, valid, avg_len, n, davg, c->stream);
+    RFA_CK(cudaGetLastError());
+    c->launches++;
+    if (mem_avg == RFA_MEM_HOST) {
+        RFA_CK(cudaMemcpyAsync(avg, davg, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        RFA_CK(cudaStreamSynchronize(c->stream));
+    }
+    return RFA_OK;
+}
+
+int rfa_ema_rows(rfa_ctx *c, const float *rows, long long row0, long long row_step, long long ring_rows,
+                 long long row_stride, long long first, long long last, float alpha, int from_state, int n, float *avg,
+                 int mem_avg) {
+    RFA_REQUIRE(c && rows && avg, "rfa_ema_rows: NULL argument");
+    RFA_REQUIRE(n > 0 && alpha > 0.0f && alpha <= 1.0f && first >= 0 && last >= first, "bad averaging request");
+    if (int rc = c->use()) return rc;
+    float *davg = avg;
+    if (mem_avg == RFA_MEM_HOST) {
+        if (int rc = c->stage[4].ensure((size_t)n * sizeof(float))) return rc;
+        davg = c->stage[4].as<float>();
+        if (from_state) RFA_CK(cudaMemcpyAsync(davg, avg, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    ema_rows(rows, row0, row_step, ring_rows, row_stride, first, last, alpha, from_state != 0, n, davg, c->stream);
     RFA_CK(cudaGetLastError());
     c->launches++;
     if (mem_avg == RFA_MEM_HOST) {

@@ -88,6 +88,58 @@ void average_rows(const float *rows, long long newest, long long dir, long long 
     cudaLaunchKernelEx(&cfg, average_rows_kernel, rows, newest, dir, ring_rows, row_stride, valid, L, N, avg);
 }
 
+// RFA_AVG_EMA (an option the reference does not have; include/rfa_b200.h): one thread per bin walks the frames in time
+// order, eight row loads in flight ahead of the dependent chain.  Joins the programmatic-dependent-launch chain of the
+// spectrum kernels like average_rows_kernel.
+__global__ void __launch_bounds__(128) ema_rows_kernel(const float *rows, long long row0, long long row_step, long long ring_rows,
+                                                       long long row_stride, long long first, long long last, float alpha,
+                                                       int from_state, int N, float *avg) {
+    launch_dependents();
+    grid_dependency_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    auto row_of = [&](long long f) {
+        long long row = row0 + f * row_step;
+        if (ring_rows > 0) {
+            row %= ring_rows;
+            if (row < 0) row += ring_rows;
+        }
+        return rows + row * row_stride + i;
+    };
+    long long f = first;
+    float a;
+    if (from_state) {
+        a = avg[i];
+    } else {
+        a = __ldcg(row_of(f));
+        f++;
+    }
+    for (; f + 8 <= last + 1; f += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldcg(row_of(f + k));
+#pragma unroll
+        for (int k = 0; k < 8; k++) a = __fadd_rn(a, __fmul_rn(alpha, __fsub_rn(v[k], a)));
+    }
+    for (; f <= last; f++) a = __fadd_rn(a, __fmul_rn(alpha, __fsub_rn(__ldcg(row_of(f)), a)));
+    avg[i] = a;
+}
+void ema_rows(const float *rows, long long row0, long long row_step, long long ring_rows, long long row_stride,
+              long long first, long long last, float alpha, bool from_state, int N, float *avg, cudaStream_t s) {
+    if (last < first) return;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((N + 127) / 128));
+    cfg.blockDim = dim3(128);
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, ema_rows_kernel, rows, row0, row_step, ring_rows, row_stride, first, last, alpha,
+                       from_state ? 1 : 0, N, avg);
+}
+
 // FftProcessor.kt:150-156: sequential float32 sum of mag[b0..b1) divided by the bin count.
 // One warp per row keeps the reference's left-to-right order inside each lane's stripe
 // only, so the result is within rounding of the reference, not bit-identical.

@@ -49,6 +49,10 @@ void reduce_peaks(const float *partial, int slots, int N, float *peaks, bool acc
 // avg[i] = (sum_{r=0..L} row(newest + r*dir)[i]) / (L+1), rows past `valid` count as -9999
 void average_rows(const float *rows, long long newest, long long dir, long long ring_rows, long long row_stride,
                   long long valid, int L, int N, float *avg, cudaStream_t s);
+// exponential average over frames first .. last (time order): a = a + alpha*(row - a), every operation rounded;
+// from_state: start from avg[] instead of the first row
+void ema_rows(const float *rows, long long row0, long long row_step, long long ring_rows, long long row_stride,
+              long long first, long long last, float alpha, bool from_state, int N, float *avg, cudaStream_t s);
 // mean dB over bins [b0, b1) of each of nrows rows (FftProcessor.kt:150-156)
 void channel_strength(const float *rows, long long row0, long long row_step, long long ring_rows,
                       long long row_stride, long long nrows, int b0, int b1, float *out, cudaStream_t s);

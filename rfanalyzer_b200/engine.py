@@ -124,6 +124,11 @@ class Context:
                                         int(row_stride), int(valid), int(avg_len), int(n), ptr(avg),
                                         _lib.MEM_DEVICE, _mem_of(avg)))
 
+    def ema_rows(self, rows, row0, row_step, ring_rows, row_stride, first, last, alpha, from_state, n, avg):
+        check(self.lib.rfa_ema_rows(self.handle, ptr(rows), int(row0), int(row_step), int(ring_rows), int(row_stride),
+                                    int(first), int(last), float(alpha), 1 if from_state else 0, int(n), ptr(avg),
+                                    _mem_of(avg)))
+
     def channel_bins(self, n, frequency, sample_rate, chan_start, chan_end):
         b0, b1 = C.c_int(), C.c_int()
         check(self.lib.rfa_channel_bins(int(n), int(frequency), int(sample_rate), int(chan_start), int(chan_end),
@@ -200,10 +205,14 @@ def synth_iq(ctx, fmt, nsamples, out, first=0, comps=None, noise_shift=2, seed=S
 class SpectrumPlan:
     """Fused IQ bytes -> dB waterfall rows (+ peak hold + time average) for one FFT size."""
 
-    def __init__(self, ctx, fmt, fft_size, window=_lib.WIN_BLACKMAN_REF, avg_len=0, peak_hold=True):
+    def __init__(self, ctx, fmt, fft_size, window=_lib.WIN_BLACKMAN_REF, avg_len=0, peak_hold=True, ema_alpha=None):
+        """ema_alpha: None = the reference's box-car mean of the newest avg_len+1 rows; a float in (0, 1] = the
+        exponential average a += alpha*(row - a) over the frames in time order (RFA_AVG_EMA)."""
         self.ctx = ctx
         self.fmt, self.fft_size, self.avg_len = fmt, int(fft_size), int(avg_len)
-        self.desc = _lib.SpectrumDesc(fmt, int(fft_size), int(window), int(avg_len), 1 if peak_hold else 0)
+        self.desc = _lib.SpectrumDesc(fmt, int(fft_size), int(window), int(avg_len), 1 if peak_hold else 0,
+                                      _lib.AVG_BOXCAR if ema_alpha is None else _lib.AVG_EMA,
+                                      0.0 if ema_alpha is None else float(ema_alpha))
         self.handle = C.c_void_p()
         check(ctx.lib.rfa_spectrum_plan_create(ctx.handle, C.byref(self.desc), C.byref(self.handle)))
 
@@ -222,10 +231,10 @@ class SpectrumPlan:
         return self.ctx.lib.rfa_spectrum_algorithmic_bytes(self.handle, int(nframes), 1 if rows_stored else 0)
 
     def process(self, iq, nframes, rows=None, peaks=None, avg=None, row0=0, row_step=1, ring_rows=0,
-                row_stride=None, history_rows=0, peaks_accumulate=False):
+                row_stride=None, history_rows=0, peaks_accumulate=False, avg_accumulate=False):
         out = _lib.SpectrumOut(ptr(rows), int(row0), int(row_step), int(ring_rows),
                                int(row_stride if row_stride is not None else self.fft_size), int(history_rows),
-                               ptr(peaks), 1 if peaks_accumulate else 0, ptr(avg))
+                               ptr(peaks), 1 if peaks_accumulate else 0, ptr(avg), 1 if avg_accumulate else 0)
         check(self.ctx.lib.rfa_spectrum_process(self.handle, ptr(iq), int(nframes), C.byref(out),
                                                 _mem_of(iq, rows, peaks, avg)))
 
@@ -233,7 +242,7 @@ class SpectrumPlan:
                      chunk_frames=0):
         """Spectrum pass over a recording on disk (rfa_spectrum_process_file): host arrays for rows (all rows
         of the range, or None), peaks and avg.  Returns the number of frames transformed."""
-        out = _lib.SpectrumOut(ptr(rows), 0, 1, 0, self.fft_size, 0, ptr(peaks), 1 if peaks_accumulate else 0, ptr(avg))
+        out = _lib.SpectrumOut(ptr(rows), 0, 1, 0, self.fft_size, 0, ptr(peaks), 1 if peaks_accumulate else 0, ptr(avg), 0)
         done = C.c_longlong()
         check(self.ctx.lib.rfa_spectrum_process_file(self.handle, path.encode(), int(first_frame), int(nframes),
                                                      C.byref(out), int(chunk_frames), C.byref(done)))
