@@ -427,6 +427,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (NCCL's version banner does,
+    # whatever NCCL_DEBUG_FILE says) are sent to stderr for the whole run, the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -575,7 +580,32 @@ def main():
     e2e_value = SAMPLES * world * e2e_steps / float(e2e_s.item()) / 1e6
     # the host-buffer path must have produced the same rows as the device path (same kernels behind it)
     e2e_ok = bool(np.array_equal(h_rows[(e2e_steps - 1) % 2][:64].numpy(), rows[(e2e_steps - 1) % 2][:64].cpu().numpy()))
-    del h_iq, h_rows
+    # ---- the ceiling of that path on this box: the same bytes per step as bare pinned copies, no kernels ---------
+    # (H2D of the IQ on one stream, D2H of the rows on another, every rank at once: what the host links of the box
+    # sustain when all N GPUs stream together; e2e above cannot exceed it)
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+    d_iq_c = torch.empty(SAMPLES * 2, dtype=torch.uint8, device="cuda")
+    d_rows_c = torch.empty((FRAMES, N_FFT), dtype=torch.float32, device="cuda")
+
+    def copy_step(k):
+        with torch.cuda.stream(s_up):
+            d_iq_c.copy_(h_iq[k % 2], non_blocking=True)
+        with torch.cuda.stream(s_down):
+            h_rows[k % 2].copy_(d_rows_c, non_blocking=True)
+    for k in range(3):
+        copy_step(k)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        copy_step(k)
+    torch.cuda.synchronize()
+    copy_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(copy_s, op=dist.ReduceOp.MAX)
+    copy_ceiling = SAMPLES * world * e2e_steps / float(copy_s.item()) / 1e6
+    copy_gbs = (SAMPLES * 6) * world * e2e_steps / float(copy_s.item()) / 1e9
+    del h_iq, h_rows, d_iq_c, d_rows_c
 
     # ---- config 5 as written: strong scaling of one long recording (after the headline buffers are freed) ------
     recording = None
@@ -623,7 +653,10 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": SAMPLES * 2,
                     "d2h_bytes_per_step": SAMPLES * 4 + 2 * N_FFT * 4, "steps": e2e_steps,
-                    "rows_equal_device_path": e2e_ok, "numa_bound_cpus": numa_cpus},
+                    "rows_equal_device_path": e2e_ok, "numa_bound_cpus": numa_cpus,
+                    "bare_copy_ceiling": {"value": copy_ceiling, "unit": UNIT, "host_link_GBps_all_gpus": copy_gbs,
+                                          "what": "the same H2D + D2H bytes per step as plain pinned cudaMemcpyAsync on two streams per "
+                                                  "GPU, all ranks at once, no kernels: the box's host-link limit for this path"}},
             "gpu_launches": int(launches) * world,
             "verified": bool(verified and e2e_ok), "verify": verify_detail,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -663,7 +696,7 @@ def main():
                                            "sample": "one pass over the 2^24-sample recording (%.1f s)" % dt}
             except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % e}
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
         if not out["verified"]:
             print("bench.py: the run's own output failed verification: %r" % (verify_detail,), file=sys.stderr)
             rc = 1
