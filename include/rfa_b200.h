@@ -366,6 +366,73 @@ int rfa_file_source_close(rfa_file_source *source);
 int rfa_spectrum_process_file(rfa_spectrum_plan *plan, const char *path, long long first_frame, long long nframes,
                               const rfa_spectrum_out *out, long long chunk_frames, long long *frames_done);
 
+/* ---- Scheduler.run as a batched runtime ------------------------------------------------
+ * A/analyzer/Scheduler.kt:140-298: per packet the squelch debounce (:161-165, SQUELCH_DEBOUNCE_COUNT = 50 :52), the
+ * recording gate (:199), the demodulator gate and mixPacketIntoSamplePacket (:237-250), the FFT buffer fill (:254-276);
+ * FftProcessor.run's channel strength (FftProcessor.kt:143-157) over [channel - width, channel + width]
+ * (AnalyzerService.kt:344-353) and squelchSatisfied = strength > squelch (AppStateRepository.kt:318-323).
+ * A call carries many packets; the loop is replayed loss-free and synchronously (csrc/scheduler.cu): no packet is
+ * dropped for lack of a buffer, a frame completed by packet k has set squelchSatisfied before packet k+1.  The
+ * waterfall ring, peak hold and average live on the device (rfa_scheduler_state; rfa_render_waterfall reads them). */
+typedef struct rfa_scheduler rfa_scheduler;
+typedef struct {
+    int format;                  /* RFA_FMT_* of the source's packets */
+    int sample_rate;             /* source.sampleRate */
+    long long source_frequency;  /* source.frequency */
+    int packet_samples;          /* source.packetSize / source.bytesPerSample (Scheduler.kt:92-94) */
+    int fft_size, window, avg_len, peak_hold; /* as rfa_spectrum_desc */
+    int ring_rows;               /* FftProcessor.kt:104: 300 / 400 / 500 */
+    int demodulation_mode;       /* RFA_MODE_OFF: isDemodulationActivated = false; else the Demodulator's mode */
+    long long channel_frequency; /* Scheduler.channelFrequency */
+    int channel_width;           /* Demodulator.channelWidth (0 = the mode's default) */
+    float volume;
+    int flags;                   /* RFA_SUM_FMA / RFA_SUM_EXACT for the chain */
+    int squelch_enabled;         /* AppStateRepository.squelchEnabled */
+    float squelch_db;            /* AppStateRepository.squelch */
+    int record_only_when_squelch_satisfied; /* Scheduler.startRecording(onlyWhenSquelchIsSatisfied) */
+} rfa_scheduler_desc;
+typedef struct {
+    long long packets;           /* out: packets consumed */
+    long long frames;            /* out: FFT frames delivered to the FftProcessor */
+    float *signal_strength;      /* host, >= frames this call can complete, or NULL: averageSignalStrength per frame */
+    unsigned char *demod_gate;   /* host [npackets] or NULL: 1 = the packet went to the demodulator */
+    unsigned char *record_gate;  /* host [npackets] or NULL: 1 = the packet would be written to the recording */
+    float *audio;                /* 48 kHz audio of the delivered packets (same memory space as the packets) */
+    long long audio_capacity;    /* >= rfa_chain_max_audio of the call's samples */
+    long long n_audio;           /* out */
+} rfa_scheduler_io;
+int rfa_scheduler_create(rfa_ctx *ctx, const rfa_scheduler_desc *desc, rfa_scheduler **out);
+int rfa_scheduler_destroy(rfa_scheduler *sched);
+/* packets: npackets * packet_samples samples, back to back (host or device per `mem`) */
+int rfa_scheduler_process(rfa_scheduler *sched, const void *packets, long long npackets, rfa_scheduler_io *io, int mem);
+/* device pointers of the FftProcessor state and the scheduler's counters; any output may be NULL.
+ * newest_row = FftProcessorData.readIndex (-1 before the first frame). */
+int rfa_scheduler_state(const rfa_scheduler *sched, float **ring, long long *newest_row, long long *valid_rows,
+                        float **peaks, float **avg, int *squelch_satisfied, int *debounce_counter, long long *packets,
+                        long long *frames);
+
+/* copies of the ring ([ring_rows][fft_size]), the peak hold and the average into HOST arrays; any may be NULL */
+int rfa_scheduler_read(rfa_scheduler *sched, float *ring, float *peaks, float *avg);
+
+/* ---- vendor real -> IQ converter ------------------------------------------------------
+ * libairspy/src/main/cpp/libairspy/iqconverter_int16.c: iqconverter_int16_create (:54-78, hb_kernel = the 47-tap
+ * HB_KERNEL_INT16 of filters.h:81-132, passed in by the caller exactly as airspy.c:920 does), _reset (:88-95),
+ * _process (:204-208 = remove_dc :160-186 + translate_fs_4 :188-202 + fir_interleaved :97-134 + delay_interleaved
+ * :136-158), _free (:80-86).  In place on `len` real int16 samples (len % 4 == 0): afterwards samples[2k], samples[2k+1]
+ * are I and Q of IQ sample k at half the rate -- the int16 IQ format RFA_FMT_S16LE of the rest of this API.
+ * Bit-exact with the reference for every input, across calls (all state is carried like the reference's struct);
+ * the delay line starts from zeros (the reference's reset clears only half of it, :94). */
+typedef struct rfa_iqconverter rfa_iqconverter;
+int rfa_iqconverter_create(rfa_ctx *ctx, const int16_t *hb_kernel, int len, rfa_iqconverter **out);
+int rfa_iqconverter_destroy(rfa_iqconverter *cnv);
+int rfa_iqconverter_reset(rfa_iqconverter *cnv);
+int rfa_iqconverter_process(rfa_iqconverter *cnv, int16_t *samples, long long len, int mem);
+/* how the DC blocker's speculative chunks fared since the last reset: chunks run, chunks re-run sequentially, chunks
+ * skipped in the blocker's dead zone (csrc/iqconv.cu explains the scheme) */
+int rfa_iqconverter_stats(rfa_iqconverter *cnv, long long *chunks, long long *rerun, long long *dead_zone);
+/* airspy.c:299-309 convert_samples_int16: raw ADC words -> (raw - 2048) << 4, the converter's input */
+int rfa_airspy_convert_samples(rfa_ctx *ctx, const uint16_t *src, int16_t *dst, long long count, int mem);
+
 /* ---- synthetic IQ (benchmark / test input; the reference ships no input fixtures) ------ */
 /* All-integer generator of SURVEY.md 8(d): sample n depends on n alone, so any segment of a
  * long recording can be produced in place on any GPU.

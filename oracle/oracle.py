@@ -117,6 +117,9 @@ def _declare(L):
                                 C.c_longlong, _u8p]),
         "orc_synth_default_comps": (C.c_int, [C.c_int, C.POINTER(SynthComp)]),
         "orc_synth_step": (C.c_uint32, [C.c_double]),
+        "orc_iqconv_new": (vp, [C.c_void_p, C.c_int]), "orc_iqconv_free": (None, [vp]), "orc_iqconv_reset": (None, [vp]),
+        "orc_iqconv_process": (None, [vp, C.c_void_p, C.c_longlong]),
+        "orc_airspy_convert_samples": (None, [C.c_void_p, C.c_void_p, C.c_longlong]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -153,6 +156,10 @@ def ref():
         L.ref_perform_fft.restype, L.ref_perform_fft.argtypes = None, [_f32p, _f32p, C.c_int]
         L.ref_perform_fft_logmag.restype, L.ref_perform_fft_logmag.argtypes = None, [_f32p, _f32p, C.c_int]
         L.ref_pffft_simd_size.restype, L.ref_pffft_simd_size.argtypes = C.c_int, []
+        L.ref_iqconv_new.restype, L.ref_iqconv_new.argtypes = C.c_void_p, [C.c_void_p, C.c_int]
+        L.ref_iqconv_free.restype, L.ref_iqconv_free.argtypes = None, [C.c_void_p]
+        L.ref_iqconv_process.restype, L.ref_iqconv_process.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_airspy_hb_kernel.restype, L.ref_airspy_hb_kernel.argtypes = C.c_int, [C.c_void_p, C.c_int]
         L.ref_spectrum_run.restype = C.c_longlong
         L.ref_spectrum_run.argtypes = [C.c_int, _u8p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int]
@@ -289,6 +296,53 @@ def spectrum_run(fmt, iq, N, L=0):
     avg = np.empty(N, dtype=np.float32)
     lib().orc_spectrum_run(fmt, iq, ns, N, L, _vp(rows), _vp(peaks), _vp(avg))
     return rows, peaks, avg
+
+
+class IqConverterInt16:
+    """iqconverter_int16 (Airspy real -> IQ): the C restatement (`use_ref=False`) or the reference's own
+    iqconverter_int16.c compiled in place (`use_ref=True`, oracle/_ref).  process() works in place like the
+    reference and returns the array."""
+
+    def __init__(self, hb_kernel, use_ref=False):
+        self.kernel = np.ascontiguousarray(hb_kernel, np.int16)
+        self.use_ref = use_ref
+        self.L = ref() if use_ref else lib()
+        new = self.L.ref_iqconv_new if use_ref else self.L.orc_iqconv_new
+        self.h = new(self.kernel.ctypes.data, len(self.kernel))
+
+    def process(self, samples):
+        assert samples.dtype == np.int16 and samples.flags.c_contiguous and len(samples) % 4 == 0
+        if self.use_ref:
+            self.L.ref_iqconv_process(self.h, samples.ctypes.data, len(samples))
+        else:
+            self.L.orc_iqconv_process(self.h, samples.ctypes.data, len(samples))
+        return samples
+
+    def __del__(self):
+        try:
+            (self.L.ref_iqconv_free if self.use_ref else self.L.orc_iqconv_free)(self.h)
+        except Exception:
+            pass
+
+
+def airspy_hb_kernel():
+    """HB_KERNEL_INT16 of the reference's libairspy/filters.h, read out of oracle/_ref (the table is compiled into
+    that library from the reference tree; it is not copied into this repository).  None when _ref is absent."""
+    if not ref_available():
+        return None
+    n = ref().ref_airspy_hb_kernel(None, 0)
+    k = np.zeros(n, np.int16)
+    ref().ref_airspy_hb_kernel(k.ctypes.data, n)
+    return k
+
+
+def synthetic_hb_kernel(ntaps=47):
+    """A half-band kernel of our own for boxes without oracle/_ref (windowed sinc, odd taps zero except the centre)."""
+    m = np.arange(ntaps) - ntaps // 2
+    h = np.sinc(m / 2.0) * np.hamming(ntaps) * 0.5
+    k = np.round(h * 32768).astype(np.int64)
+    k[(m % 2 == 0) & (m != 0)] = 0
+    return np.clip(k, -32768, 32767).astype(np.int16)
 
 
 def ema_rows(rows, alpha, init=None):

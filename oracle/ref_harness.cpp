@@ -150,3 +150,26 @@ extern "C" __attribute__((visibility("default"))) long long ref_spectrum_run(
     free(partial);
     return F;
 }
+
+
+/* ---- the reference's Airspy real -> IQ converter, compiled in place (libairspy/.../iqconverter_int16.c) ----------
+ * ref_iqconv_new zeroes the whole delay line: the reference's reset clears only half of it (iqconverter_int16.c:94,
+ * `cnv->len * sizeof(int16_t) / 4` bytes of a `cnv->len * sizeof(int32_t) / 4`-byte block), so its first len/4 odd
+ * outputs would otherwise be whatever malloc returned. */
+extern "C" {
+#include "iqconverter_int16.h"
+}
+#include "filters.h"
+extern "C" __attribute__((visibility("default"))) void *ref_iqconv_new(const int16_t *hb_kernel, int len) {
+    iqconverter_int16_t *c = iqconverter_int16_create(hb_kernel, len);
+    memset(c->delay_line, 0, (size_t)c->len * sizeof(int32_t) / 4);
+    return c;
+}
+extern "C" __attribute__((visibility("default"))) void ref_iqconv_free(void *c) { iqconverter_int16_free((iqconverter_int16_t *)c); }
+extern "C" __attribute__((visibility("default"))) void ref_iqconv_process(void *c, int16_t *samples, int len) {
+    iqconverter_int16_process((iqconverter_int16_t *)c, samples, len);
+}
+extern "C" __attribute__((visibility("default"))) int ref_airspy_hb_kernel(int16_t *out, int capacity) {
+    if (out && capacity >= HB_KERNEL_INT16_LEN) memcpy(out, HB_KERNEL_INT16, sizeof(HB_KERNEL_INT16));
+    return HB_KERNEL_INT16_LEN;
+}

@@ -1353,3 +1353,87 @@ long long orc_chain_run(int fmt, const uint8_t *iq, long long nsamples, int samp
     orc_converter_free(c);
     return nAudio;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Airspy real -> IQ converter, restated from iqconverter_int16.c (line references in rfa_oracle.h).
+ * ------------------------------------------------------------------------------------------------ */
+struct orc_iqconv {
+    int len;            /* cnv->len = len/2 + 1 (:60) */
+    int32_t *kernel;    /* hb_kernel[2*i] (:72-75) */
+    int32_t *queue;     /* the newest cnv->len even samples, newest first */
+    int16_t *delay;     /* cnv->len >> 1 odd samples */
+    int delay_index;
+    int16_t old_x, old_y;
+    int32_t old_e;
+};
+
+orc_iqconv *orc_iqconv_new(const int16_t *hb_kernel, int len) {
+    orc_iqconv *c = (orc_iqconv *)calloc(1, sizeof(*c));
+    c->len = len / 2 + 1;
+    c->kernel = (int32_t *)calloc((size_t)c->len, sizeof(int32_t));
+    c->queue = (int32_t *)calloc((size_t)c->len, sizeof(int32_t));
+    c->delay = (int16_t *)calloc((size_t)c->len, sizeof(int16_t));
+    for (int i = 0; i < c->len; i++) c->kernel[i] = hb_kernel[i * 2];
+    return c;
+}
+void orc_iqconv_free(orc_iqconv *c) {
+    if (!c) return;
+    free(c->kernel);
+    free(c->queue);
+    free(c->delay);
+    free(c);
+}
+void orc_iqconv_reset(orc_iqconv *c) {
+    c->delay_index = 0;
+    c->old_x = c->old_y = 0;
+    c->old_e = 0;
+    memset(c->queue, 0, sizeof(int32_t) * (size_t)c->len);
+    memset(c->delay, 0, sizeof(int16_t) * (size_t)c->len);
+}
+void orc_iqconv_process(orc_iqconv *c, int16_t *samples, long long len) {
+    /* remove_dc (:160-186) */
+    int16_t old_x = c->old_x, old_y = c->old_y;
+    int32_t old_e = c->old_e;
+    for (long long i = 0; i < len; i++) {
+        int16_t x = samples[i];
+        int16_t w = (int16_t)(x - old_x);
+        int32_t u = old_e + (int32_t)old_y * 32100;
+        int16_t s = (int16_t)(u >> 15);
+        int16_t y = (int16_t)(w + s);
+        old_e = u - (int32_t)((uint32_t)(int32_t)s << 15);
+        old_x = x;
+        old_y = y;
+        samples[i] = y;
+    }
+    c->old_x = old_x;
+    c->old_y = old_y;
+    c->old_e = old_e;
+    /* translate_fs_4 (:188-198) */
+    for (long long i = 0; i + 3 < len; i += 4) {
+        samples[i + 0] = (int16_t)(-samples[i + 0]);
+        samples[i + 1] = (int16_t)(-samples[i + 1] >> 1);
+        samples[i + 3] = (int16_t)(samples[i + 3] >> 1);
+    }
+    /* fir_interleaved (:97-134): queue[j] = the even sample j steps ago */
+    for (long long i = 0; i < len; i += 2) {
+        memmove(c->queue + 1, c->queue, sizeof(int32_t) * (size_t)(c->len - 1));
+        c->queue[0] = samples[i];
+        uint32_t acc = 0; /* int32 accumulation, wrap-around made explicit */
+        for (int j = 0; j < c->len; j++) acc += (uint32_t)(c->kernel[j] * c->queue[j]);
+        samples[i] = (int16_t)((int32_t)acc >> 15);
+    }
+    /* delay_interleaved on samples + 1 (:136-158) */
+    int half = c->len >> 1, index = c->delay_index;
+    for (long long i = 1; i < len + 1 && i - 1 < len; i += 2) {
+        if (i >= len) break;
+        int16_t res = c->delay[index];
+        c->delay[index] = samples[i];
+        samples[i] = res;
+        if (++index >= half) index = 0;
+    }
+    c->delay_index = index;
+}
+void orc_airspy_convert_samples(const uint16_t *src, int16_t *dst, long long count) {
+    for (long long i = 0; i < count; i++) dst[i] = (int16_t)(((int)src[i] - 2048) << 4);
+}

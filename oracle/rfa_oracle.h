@@ -208,4 +208,17 @@ uint32_t orc_synth_step(double cyclesPerSample);
 #ifdef __cplusplus
 }
 #endif
+
+/* ---- Airspy real -> IQ converter (libairspy/src/main/cpp/libairspy/iqconverter_int16.c:54-208), restated.
+ * Integer arithmetic throughout: DC removal with error feedback (:160-186), fs/4 translation (:188-202), the
+ * half-band FIR on the even samples (:97-134, kernel = every other tap), a len/4-sample delay on the odd ones
+ * (:136-158).  The reference clears only half of its delay line on reset (:94); the restatement starts from zeros. */
+typedef struct orc_iqconv orc_iqconv;
+orc_iqconv *orc_iqconv_new(const int16_t *hb_kernel, int len);
+void orc_iqconv_free(orc_iqconv *c);
+void orc_iqconv_reset(orc_iqconv *c);
+void orc_iqconv_process(orc_iqconv *c, int16_t *samples, long long len);
+/* airspy.c:299-309 convert_samples_int16: (raw - 2048) << 4 */
+void orc_airspy_convert_samples(const uint16_t *src, int16_t *dst, long long count);
+
 #endif

@@ -16,7 +16,8 @@ from . import dsp
 from . import detect
 from .dsp import (SamplePacket, Signed8BitIQConverter, Unsigned8BitIQConverter, Signed16BitIQConverter, NativeDsp,
                   FftProcessor, FftProcessorData, FirFilter, ComplexFirFilter, RationalResampler, Demodulator, AudioSink,
-                  ChainPlan, FileIQSource, parse_recording_name, recording_file_name)
+                  ChainPlan, FileIQSource, parse_recording_name, recording_file_name, IqConverterInt16, Scheduler,
+                  airspy_convert_samples)
 
 __all__ = ["Context", "SpectrumPlan", "RfaError", "FMT_S8", "FMT_U8", "FMT_S16LE", "WIN_BLACKMAN_REF",
            "WIN_HANN", "WIN_RECT", "MEM_HOST", "MEM_DEVICE", "BYTES_PER_SAMPLE"]

@@ -65,6 +65,20 @@ class ChainDesc(C.Structure):
                 ("packet_samples", C.c_int), ("volume", C.c_float), ("flags", C.c_int)]
 
 
+class SchedulerDesc(C.Structure):
+    _fields_ = [("format", C.c_int), ("sample_rate", C.c_int), ("source_frequency", C.c_longlong),
+                ("packet_samples", C.c_int), ("fft_size", C.c_int), ("window", C.c_int), ("avg_len", C.c_int),
+                ("peak_hold", C.c_int), ("ring_rows", C.c_int), ("demodulation_mode", C.c_int),
+                ("channel_frequency", C.c_longlong), ("channel_width", C.c_int), ("volume", C.c_float), ("flags", C.c_int),
+                ("squelch_enabled", C.c_int), ("squelch_db", C.c_float), ("record_only_when_squelch_satisfied", C.c_int)]
+
+
+class SchedulerIO(C.Structure):
+    _fields_ = [("packets", C.c_longlong), ("frames", C.c_longlong), ("signal_strength", C.c_void_p),
+                ("demod_gate", C.c_void_p), ("record_gate", C.c_void_p), ("audio", C.c_void_p),
+                ("audio_capacity", C.c_longlong), ("n_audio", C.c_longlong)]
+
+
 class DetectWindow(C.Structure):
     """rfa_detect_window: (row, first bin, last bin inclusive)."""
     _fields_ = [("row", C.c_longlong), ("start", C.c_int), ("end", C.c_int)]
@@ -154,6 +168,17 @@ SIGNATURES = {
     "rfa_chain_max_audio": (_ll, [_vp, _ll]),
     "rfa_chain_process": (_i, [_vp, _vp, _ll, _vp, _ll, _pll, _i]),
     "rfa_chain_seek": (_i, [_vp, _ll, _pll]),
+    "rfa_scheduler_create": (_i, [_vp, C.POINTER(SchedulerDesc), _pvp]),
+    "rfa_scheduler_destroy": (_i, [_vp]),
+    "rfa_scheduler_process": (_i, [_vp, _vp, _ll, C.POINTER(SchedulerIO), _i]),
+    "rfa_scheduler_state": (_i, [_vp, _pvp, _pll, _pll, _pvp, _pvp, _pi, _pi, _pll, _pll]),
+    "rfa_scheduler_read": (_i, [_vp, _vp, _vp, _vp]),
+    "rfa_iqconverter_create": (_i, [_vp, _vp, _i, _pvp]),
+    "rfa_iqconverter_destroy": (_i, [_vp]),
+    "rfa_iqconverter_reset": (_i, [_vp]),
+    "rfa_iqconverter_process": (_i, [_vp, _vp, _ll, _i]),
+    "rfa_iqconverter_stats": (_i, [_vp, _pll, _pll, _pll]),
+    "rfa_airspy_convert_samples": (_i, [_vp, _vp, _vp, _ll, _i]),
     "rfa_synth_iq": (_i, [_vp, _i, C.c_uint32, C.POINTER(SynthComp), _i, _i, _ll, _ll, _vp, _i]),
 }
 

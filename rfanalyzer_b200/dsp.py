@@ -592,6 +592,114 @@ class ChainPlan:
         return n.value
 
 
+class Scheduler:
+    """Scheduler.run (A/analyzer/Scheduler.kt:140-298) over batches of packets: rfa_scheduler_*.  Field names follow
+    the reference (channelFrequency, isDemodulationActivated, squelchSatisfied)."""
+    SQUELCH_DEBOUNCE_COUNT = 50
+
+    def __init__(self, ctx, fmt, sampleRate, frequency, packetSamples, fftSize, window=_lib.WIN_BLACKMAN_REF, avg_len=0,
+                 peak_hold=True, ring_rows=300, mode=_lib.MODE_OFF, channelFrequency=0, channelWidth=0, volume=1.0,
+                 flags=_lib.SUM_FMA, squelchEnabled=False, squelch=-30.0, recordOnlyWhenSquelchIsSatisfied=False):
+        self.ctx = ctx
+        self.desc = _lib.SchedulerDesc(int(fmt), int(sampleRate), int(frequency), int(packetSamples), int(fftSize), int(window),
+                                       int(avg_len), 1 if peak_hold else 0, int(ring_rows), int(mode), int(channelFrequency),
+                                       int(channelWidth), float(volume), int(flags), 1 if squelchEnabled else 0,
+                                       float(squelch), 1 if recordOnlyWhenSquelchIsSatisfied else 0)
+        self.handle = C.c_void_p()
+        check(ctx.lib.rfa_scheduler_create(ctx.handle, C.byref(self.desc), C.byref(self.handle)))
+        self.isDemodulationActivated = mode != _lib.MODE_OFF
+
+    def max_audio(self, npackets):
+        n = npackets * self.desc.packet_samples
+        return int(n * 48000.0 / self.desc.sample_rate) + 64 * (npackets + 1)
+
+    def process(self, packets, npackets, audio=None):
+        """-> dict(frames, signal_strength[frames], demod_gate[npackets], record_gate[npackets], n_audio)."""
+        from .engine import _mem_of
+        max_frames = npackets * max(1, self.desc.packet_samples // self.desc.fft_size + 1) + 1
+        strength = np.empty(max_frames, np.float32)
+        dem, rec = np.zeros(npackets, np.uint8), np.zeros(npackets, np.uint8)
+        cap = 0 if audio is None else (audio.numel() if hasattr(audio, "numel") else len(audio))
+        io = _lib.SchedulerIO(0, 0, ptr(strength), ptr(dem), ptr(rec), ptr(audio), cap, 0)
+        check(self.ctx.lib.rfa_scheduler_process(self.handle, ptr(packets), int(npackets), C.byref(io),
+                                                 _mem_of(packets, audio)))
+        return {"frames": io.frames, "signal_strength": strength[: io.frames].copy(), "demod_gate": dem, "record_gate": rec,
+                "n_audio": io.n_audio}
+
+    def state(self):
+        """Device addresses of ring / peaks / avg and the counters (rfa_scheduler_state)."""
+        ring, peaks, avg = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        newest, valid, pk, fr = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_longlong()
+        sq, db = C.c_int(), C.c_int()
+        check(self.ctx.lib.rfa_scheduler_state(self.handle, C.byref(ring), C.byref(newest), C.byref(valid), C.byref(peaks),
+                                               C.byref(avg), C.byref(sq), C.byref(db), C.byref(pk), C.byref(fr)))
+        return {"ring": ring.value, "newest_row": newest.value, "valid_rows": valid.value, "peaks": peaks.value,
+                "avg": avg.value, "squelchSatisfied": bool(sq.value), "squelchDebounceCounter": db.value,
+                "packets": pk.value, "frames": fr.value}
+
+    def copy_state(self):
+        """(ring[ring_rows][fft_size], peaks, avg) as numpy arrays (rfa_scheduler_read)."""
+        n, rows = self.desc.fft_size, self.desc.ring_rows
+        ring, peaks, avg = np.empty((rows, n), np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+        check(self.ctx.lib.rfa_scheduler_read(self.handle, ptr(ring), ptr(peaks), ptr(avg)))
+        return ring, peaks, avg
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.rfa_scheduler_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class IqConverterInt16:
+    """iqconverter_int16 (libairspy/.../iqconverter_int16.c:54-208): Airspy / HydraSDR real ADC samples -> int16 IQ,
+    in place, state carried across calls.  `samples`: int16 numpy array or CUDA tensor (viewed as int16)."""
+
+    def __init__(self, ctx, hb_kernel):
+        self.ctx = ctx
+        k = np.ascontiguousarray(hb_kernel, np.int16)
+        self.handle = C.c_void_p()
+        check(ctx.lib.rfa_iqconverter_create(ctx.handle, ptr(k), len(k), C.byref(self.handle)))
+
+    def reset(self):
+        check(self.ctx.lib.rfa_iqconverter_reset(self.handle))
+
+    def process(self, samples, length=None):
+        from .engine import _mem_of
+        n = int(length if length is not None else (samples.numel() if hasattr(samples, "numel") else len(samples)))
+        check(self.ctx.lib.rfa_iqconverter_process(self.handle, ptr(samples), n, _mem_of(samples)))
+        return samples
+
+    def stats(self):
+        """(chunks, chunks re-run sequentially, chunks skipped in the DC blocker's dead zone) since the last reset."""
+        v = [C.c_longlong() for _ in range(3)]
+        check(self.ctx.lib.rfa_iqconverter_stats(self.handle, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.rfa_iqconverter_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def airspy_convert_samples(ctx, src, dst):
+    """airspy.c:299-309: raw 12-bit ADC words (uint16) -> (raw - 2048) << 4 (int16)."""
+    from .engine import _mem_of
+    n = src.numel() if hasattr(src, "numel") else len(src)
+    check(ctx.lib.rfa_airspy_convert_samples(ctx.handle, ptr(src), ptr(dst), int(n), _mem_of(src, dst)))
+
+
 # ---- recordings on disk (SURVEY.md 8f rank 1) ---------------------------------------------------------------
 FILE_HACKRF, FILE_RTLSDR, FILE_AIRSPY, FILE_HYDRASDR = range(4)   # FilesourceFileFormat
 

@@ -309,3 +309,22 @@ def test_chain_produces_audio(oracle, mode, fs, cw, fmt, packet):
     expect = n * 48000.0 / fs
     assert abs(len(audio) - expect) <= 8 + 0.02 * expect
     assert np.all(np.isfinite(audio))
+
+
+def test_iqconverter_restatement_equals_the_compiled_reference(oracle):
+    """iqconverter_int16.c (libairspy) compiled in place vs the C restatement: identical int16 output for noise,
+    full-scale square waves (int16 wrap-around), silence and constant input, across ragged calls."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref is not built (no reference tree on this box)")
+    rng = np.random.default_rng(5)
+    k = oracle.airspy_hb_kernel()
+    assert len(k) == 47 and k[23] == 16384 and k[1] == 0
+    n = 60_000
+    t = np.arange(n)
+    sigs = [rng.integers(-32768, 32768, n), (rng.integers(0, 4096, n) - 2048) << 4, np.where(t % 5 < 2, -32768, 32767),
+            np.zeros(n), np.full(n, -777)]
+    for sig in sigs:
+        x = sig.astype(np.int16)
+        a, b = oracle.IqConverterInt16(k, use_ref=False), oracle.IqConverterInt16(k, use_ref=True)
+        for lo, hi in ((0, 4), (4, 20000), (20000, 20008), (20008, n)):
+            assert np.array_equal(a.process(x[lo:hi].copy()), b.process(x[lo:hi].copy()))
