@@ -439,6 +439,7 @@ struct rfa_chain {
     // rfa_chain_process advances the streaming state stage by stage; a failure in the middle of a call leaves
     // the stages out of step, so the chain refuses further packets until rfa_chain_seek re-positions it
     bool poisoned = false;
+    int carry_cur = 0;  // which half of fm_carry holds the previous call's last filtered sample
 };
 
 extern "C" {
@@ -542,9 +543,9 @@ int rfa_chain_create(rfa_ctx *c, const rfa_chain_desc *d, rfa_chain **out) {
             if ((rc = rfa_fir_create(c, t1.data(), nullptr, (int)t1.size(), 2, d->flags, &ch->audio1))) break;
             if ((rc = rfa_fir_create(c, t2.data(), nullptr, (int)t2.size(), 4, d->flags, &ch->audio2))) break;
         }
-        if ((rc = ch->fm_carry.ensure(2 * sizeof(float)))) break;
+        if ((rc = ch->fm_carry.ensure(4 * sizeof(float)))) break;
         if ((rc = ch->agc_state.ensure(sizeof(float)))) break;
-        RFA_CK(cudaMemsetAsync(ch->fm_carry.p, 0, 2 * sizeof(float), c->stream));
+        RFA_CK(cudaMemsetAsync(ch->fm_carry.p, 0, 4 * sizeof(float), c->stream));
         RFA_CK(cudaMemsetAsync(ch->agc_state.p, 0, sizeof(float), c->stream));
     } while (0);
     if (rc) {
@@ -594,7 +595,8 @@ int rfa_chain_seek(rfa_chain *ch, long long sample_index, long long *audio_index
     ch->rs->rel = 0;
     ch->rs->ph = 0;
     if (int rc = ch->rs->h.reset(c)) return rc;
-    RFA_CK(cudaMemsetAsync(ch->fm_carry.p, 0, 2 * sizeof(float), c->stream));
+    RFA_CK(cudaMemsetAsync(ch->fm_carry.p, 0, 4 * sizeof(float), c->stream));
+    ch->carry_cur = 0;
     RFA_CK(cudaMemsetAsync(ch->agc_state.p, 0, sizeof(float), c->stream));
     // counters: the same arithmetic rfa_chain_process applies, for sample_index inputs in one step
     const long long n = sample_index;
@@ -696,6 +698,92 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
         if (int rc = resampler_run(ch->rs, in, nsamples, ch->q_re.p(), ch->q_im.p(), nq, &got, &cons)) return rc;
         ch->nco_idx = (int)((ch->nco_idx + nsamples) % ch->nco_len);
     }
+    // ---- FM modes: user filter, discriminator, volume and audio decimators in ONE launch (chain_fused.cu) --------
+    if (mode == RFA_MODE_NFM || mode == RFA_MODE_WFM) {
+        const int ratio = ch->quad_rate / kAudioRate;  // 8 (wFM) or 2 (nFM): both decimators / the first one only
+        rfa_fir *u = ch->user, *f1 = ch->audio1, *f2 = ch->audio2;
+        const long long n1 = ratio >= 2 ? f1->count(nu) : 0, n2 = ratio == 8 ? f2->count(n1) : 0;
+        const long long nfinal = ratio == 8 ? n2 : (ratio == 2 ? n1 : nu);
+        RFA_REQUIRE(nfinal <= capacity, "internal: audio count %lld exceeds capacity %lld", nfinal, capacity);
+        if (int rc = ch->dem.ensure(nu)) return rc;
+        if (int rc = ch->a1.ensure(n1)) return rc;
+        float *d_audio = audio;
+        if (mem == RFA_MEM_HOST) {
+            if (int rc = ch->a2.ensure(nfinal)) return rc;
+            d_audio = ch->a2.p();
+        }
+        const float max_dev = ch->channel_width * (mode == RFA_MODE_NFM ? 0.75f : 0.85f);  // Demodulator.kt:175-176
+        FmTailArgs fa{};
+        fa.q_re = ch->q_re.p();
+        fa.q_im = ch->q_im.p();
+        fa.hist_u_re = u->h.re[u->h.cur].as<float>();
+        fa.hist_u_im = u->h.im[u->h.cur].as<float>();
+        fa.user_hist = u->h.hist;
+        fa.user_taps = u->ntaps;
+        fa.taps_user = u->taps_re.as<float>();
+        fa.first_u = u->first;
+        fa.nu = nu;
+        fa.carry_in = ch->fm_carry.as<float>() + 2 * ch->carry_cur;
+        fa.carry_out = ch->fm_carry.as<float>() + 2 * (ch->carry_cur ^ 1);
+        fa.gain = ch->quad_rate / (float)(2 * 3.14159265358979323846 * (double)max_dev);  // :256
+        fa.volume = ch->d.volume;
+        fa.ratio = ratio;
+        fa.taps_a1 = f1->taps_re.as<float>();
+        fa.taps_a2 = f2->taps_re.as<float>();
+        fa.a1_taps = f1->ntaps;
+        fa.a2_taps = f2->ntaps;
+        fa.a1_hist = f1->h.hist;
+        fa.a2_hist = f2->h.hist;
+        fa.hist_a1 = f1->h.re[f1->h.cur].as<float>();
+        fa.hist_a2 = f2->h.re[f2->h.cur].as<float>();
+        fa.first_a1 = f1->first;
+        fa.first_a2 = f2->first;
+        fa.n1 = n1;
+        fa.n2 = n2;
+        fa.dem_out = ch->dem.p();
+        fa.a1_out = ch->a1.p();
+        fa.audio = d_audio;
+        cudaError_t e = fm_tail_launch(fa, ch->exact, c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "fused FM kernel");
+        // the delay lines of the three filters slide in one launch; counters like FirFilter.filter leaves them
+        ChainStateArgs sa{};
+        auto line = [&](int i, rfa_fir *f, const float *in_re, const float *in_im, long long n) {
+            ChainStateArgs::Line &l = sa.line[i];
+            l.in_re = in_re;
+            l.in_im = in_im;
+            l.old_re = f->h.re[f->h.cur].as<float>();
+            l.old_im = in_im ? f->h.im[f->h.cur].as<float>() : nullptr;
+            l.new_re = f->h.re[f->h.cur ^ 1].as<float>();
+            l.new_im = in_im ? f->h.im[f->h.cur ^ 1].as<float>() : nullptr;
+            l.n = n;
+            l.hist = n > 0 ? f->h.hist : 0;
+        };
+        line(0, u, ch->q_re.p(), ch->q_im.p(), nq);
+        line(1, f1, ch->dem.p(), nullptr, ratio >= 2 ? nu : 0);
+        line(2, f2, ch->a1.p(), nullptr, ratio == 8 ? n1 : 0);
+        e = chain_state_launch(sa, c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "chain state kernel");
+        c->launches += nu > 0 ? 2 : 1;
+        if (nq > 0) u->h.cur ^= 1;
+        u->first = u->first + nu * u->dec - nq;
+        if (nu > 0) ch->carry_cur ^= 1;
+        if (ratio >= 2) {
+            if (nu > 0) f1->h.cur ^= 1;
+            f1->first = f1->first + n1 * f1->dec - nu;
+        }
+        if (ratio == 8) {
+            if (n1 > 0) f2->h.cur ^= 1;
+            f2->first = f2->first + n2 * f2->dec - n1;
+        }
+        if (mem == RFA_MEM_HOST) {
+            if (nfinal) RFA_CK(cudaMemcpyAsync(audio, d_audio, nfinal * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            RFA_CK(cudaStreamSynchronize(c->stream));
+        }
+        // device mode: nothing of this call lives on the host, the call stays asynchronous on the context's stream
+        *n_audio = nfinal;
+        guard.ok = true;
+        return RFA_OK;
+    }
     // ---- K5: user (channel) filter ---------------------------------------------------------------
     if (int rc = ch->u_re.ensure(nu)) return rc;
     if (int rc = ch->u_im.ensure(nu)) return rc;
@@ -718,17 +806,7 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
         for (long long p = 0; p < npk; p++) m = off[p + 1] - off[p] > m ? off[p + 1] - off[p] : m;
         return m;
     };
-    if (mode == RFA_MODE_NFM || mode == RFA_MODE_WFM) {
-        if (int rc = ch->dem.ensure(nu)) return rc;
-        const float max_dev = ch->channel_width * (mode == RFA_MODE_NFM ? 0.75f : 0.85f);  // Demodulator.kt:175-176
-        const float gain = ch->quad_rate / (float)(2 * 3.14159265358979323846 * (double)max_dev);  // :256
-        cudaError_t e = demod_fm_launch(ch->u_re.p(), ch->u_im.p(), nu, ch->fm_carry.as<float>(), gain, volume,
-                                        ch->dem.p(), ch->exact, c->num_sms, c->stream);
-        if (e != cudaSuccess) return cuda_fail(e, "fm kernel");
-        c->launches += nu > 0 ? 2 : 0;
-        dem = ch->dem.p();
-        ndem = nu;
-    } else if (mode == RFA_MODE_AM) {
+    if (mode == RFA_MODE_AM) {
         if (int rc = ch->dem.ensure(nu)) return rc;
         if (int rc = ch->agc_scratch.ensure(4 * (size_t)npk * sizeof(float))) return rc;
         if (int rc = upload_segments(u_off)) return rc;

@@ -1,0 +1,195 @@
+// chain_fused.cu -- everything behind the resampler of an FM chain in ONE kernel:
+//   Demodulator.applyUserFilter   (A/analyzer/Demodulator.kt:215-240)  27-tap low pass on the quadrature samples
+//   Demodulator.demodulateFM      (:251-275)                           gain * atan2 of x[n] * conj(x[n-1]), one sample of carry
+//   Demodulator.run volume        (:184-187)
+//   AudioSink.applyAudioFilter    (A/analyzer/AudioSink.java:215-237)  the /2 (and /4) audio decimators
+// Round 1 ran them as four FIR / demodulator launches plus a state kernel each: nine launches
+// behind the resampler for a few MB of data.  Here a CTA owns a run of TILE demodulator samples: it stages the
+// quadrature samples that run needs (with the halo of every filter behind it), runs the user filter, the
+// discriminator and the decimators out of shared memory, and writes each intermediate sample it OWNS once -- the
+// demodulated stream and the first decimator's output still go to global memory, because they are the delay lines
+// ("history") of the next call.  The arithmetic per output is the same as fir.cu / demod.cu: taps in the reference's
+// order, SUM_EXACT with separately rounded products and sums and a double-precision atan2.
+//
+// A second small kernel slides every delay line of the chain in one launch.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "kernels.h"
+
+namespace rfa {
+namespace {
+
+template <bool EXACT>
+__device__ __forceinline__ float mac(float acc, float a, float b) {
+    return EXACT ? __fadd_rn(acc, __fmul_rn(a, b)) : fmaf(a, b, acc);
+}
+
+constexpr int TILE = 2048;     // demodulator samples owned by a CTA
+constexpr int HALO = 40;       // >= 1 (discriminator) + 8 (first decimator) + 2 * 12 (second) demodulator samples before the run
+constexpr int UT = 32;         // user filter taps at most (27 in the reference)
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
+    __shared__ float s_qre[TILE + HALO + UT], s_qim[TILE + HALO + UT];  // quadrature samples (user filter input)
+    __shared__ float s_ure[TILE + HALO], s_uim[TILE + HALO];            // user filter output
+    __shared__ float s_dem[TILE + HALO];                                // demodulated (index 0 = u0 - HALO + 1)
+    __shared__ float s_a1[(TILE + HALO) / 2 + 2];                       // first decimator output
+    __shared__ float s_tu[UT], s_t1[16], s_t2[16];
+    const long long u0 = (long long)blockIdx.x * TILE;                  // first demodulator index this CTA owns
+    long long u1 = u0 + TILE;
+    if (u1 > a.nu) u1 = a.nu;
+    if (u0 >= u1) return;
+    for (int t = threadIdx.x; t < a.user_taps; t += blockDim.x) s_tu[t] = a.taps_user[t];
+    if (threadIdx.x < a.a1_taps) s_t1[threadIdx.x] = a.taps_a1[threadIdx.x];
+    if (threadIdx.x < a.a2_taps) s_t2[threadIdx.x] = a.taps_a2[threadIdx.x];
+    // ---- quadrature samples: user output i needs inputs first_u + i - (taps-1) .. first_u + i (decimation 1) ----
+    const long long ulo = u0 - HALO;                                    // first user output computed here (may be < 0)
+    const long long qlo = a.first_u + ulo - (a.user_taps - 1);
+    const int nqs = (int)(u1 - ulo) + a.user_taps - 1;
+    for (int s = threadIdx.x; s < nqs; s += blockDim.x) {
+        const long long k = qlo + s;
+        float r = 0.0f, q = 0.0f;
+        if (k >= 0) {
+            r = a.q_re[k];
+            q = a.q_im[k];
+        } else if (k + a.user_hist >= 0) {
+            r = a.hist_u_re[k + a.user_hist];
+            q = a.hist_u_im[k + a.user_hist];
+        }
+        s_qre[s] = r;
+        s_qim[s] = q;
+    }
+    __syncthreads();
+    // ---- user filter (FirFilter.kt:90-96), outputs ulo .. u1-1; outputs with index < 0 belong to earlier calls ----
+    const int nus = (int)(u1 - ulo);
+    for (int s = threadIdx.x; s < nus; s += blockDim.x) {
+        float ar = 0.0f, ai = 0.0f;
+        if (ulo + s >= 0) {
+            const int pos = s + a.user_taps - 1;
+            for (int t = 0; t < a.user_taps; t++) {
+                const float h = s_tu[t];
+                ar = mac<EXACT>(ar, h, s_qre[pos - t]);
+                ai = mac<EXACT>(ai, h, s_qim[pos - t]);
+            }
+        } else if (ulo + s == -1) {  // the sample before this call's first one: the discriminator's carry
+            ar = a.carry_in[0];
+            ai = a.carry_in[1];
+        }
+        s_ure[s] = ar;
+        s_uim[s] = ai;
+    }
+    __syncthreads();
+    // ---- discriminator (Demodulator.kt:262-270) for demodulator indices ulo+1 .. u1-1 ----
+    for (int s = threadIdx.x + 1; s < nus; s += blockDim.x) {
+        const long long i = ulo + s;
+        float d = 0.0f;
+        if (i >= 0) {
+            const float r = s_ure[s], q = s_uim[s], pr = s_ure[s - 1], pq = s_uim[s - 1];
+            if (EXACT) {
+                const float x = __fadd_rn(__fmul_rn(r, pr), __fmul_rn(q, pq));
+                const float y = __fsub_rn(__fmul_rn(q, pr), __fmul_rn(r, pq));
+                d = __fmul_rn(__fmul_rn(a.gain, (float)atan2((double)y, (double)x)), a.volume);
+            } else {
+                d = a.gain * atan2f(fmaf(q, pr, -(r * pq)), fmaf(r, pr, q * pq)) * a.volume;
+            }
+            if (i >= u0) {
+                if (a.dem_out) a.dem_out[i] = d;
+                if (a.ratio == 1) a.audio[i] = d;
+            }
+        } else if (i + a.a1_hist >= 0 && a.hist_a1) {
+            d = a.hist_a1[i + a.a1_hist];  // demodulated samples of earlier calls: the first decimator's delay line
+        }
+        s_dem[s] = d;
+    }
+    if (threadIdx.x == 0 && u1 == a.nu) {  // Demodulator.kt:271-272: the newest filtered sample is the next call's carry
+        a.carry_out[0] = s_ure[nus - 1];
+        a.carry_out[1] = s_uim[nus - 1];
+    }
+    if (a.ratio == 1) return;
+    __syncthreads();
+    // ---- first decimator (FirFilter.kt:141-146): output m <-> demodulator index first_a1 + 2*m ----
+    // computed here: every m whose newest tap lies in (ulo + 8, u1); owned: newest tap in [u0, u1)
+    const long long dlo = ulo + 1;  // demodulator index of s_dem[1]
+    long long m_lo = (dlo + (a.a1_taps - 1) - a.first_a1 + 1) / 2;  // ceil((dlo + taps-1 - first) / 2)
+    if ((dlo + (a.a1_taps - 1) - a.first_a1) < 0) m_lo = -((-(dlo + (a.a1_taps - 1) - a.first_a1)) / 2);
+    long long m_hi = (u1 - 1 - a.first_a1) >= 0 ? (u1 - 1 - a.first_a1) / 2 : -1;  // last m with newest tap <= u1-1
+    const int nm = (int)(m_hi - m_lo + 1);
+    for (int s = threadIdx.x; s < nm; s += blockDim.x) {
+        const long long m = m_lo + s;
+        float v = 0.0f;
+        if (m >= 0) {
+            const long long newest = a.first_a1 + 2 * m;
+            const int pos = (int)(newest - dlo) + 1;
+            float acc = 0.0f;
+            for (int t = 0; t < a.a1_taps; t++) acc = mac<EXACT>(acc, s_t1[t], s_dem[pos - t]);
+            v = acc;
+            if (newest >= u0 && m < a.n1) {
+                if (a.a1_out) a.a1_out[m] = v;
+                if (a.ratio == 2) a.audio[m] = v;
+            }
+        } else if (m + a.a2_hist >= 0 && a.hist_a2) {
+            v = a.hist_a2[m + a.a2_hist];  // first-decimator outputs of earlier calls: the second decimator's delay line
+        }
+        s_a1[s] = v;
+    }
+    if (a.ratio != 8) return;
+    __syncthreads();
+    // ---- second decimator: output b <-> first-decimator index first_a2 + 4*b; owned when that sample's newest
+    // demodulator index lies in [u0, u1) ----
+    if (nm <= 0) return;
+    // b range whose window [newest-12, newest] lies inside [m_lo, m_hi] and whose newest sample is owned
+    long long b_lo = (m_lo + (a.a2_taps - 1) - a.first_a2 + 3) / 4;
+    if ((m_lo + (a.a2_taps - 1) - a.first_a2) < 0) b_lo = -((-(m_lo + (a.a2_taps - 1) - a.first_a2)) / 4);
+    if (b_lo < 0) b_lo = 0;
+    const long long b_hi = (m_hi - a.first_a2) >= 0 ? (m_hi - a.first_a2) / 4 : -1;
+    for (long long b = b_lo + threadIdx.x; b <= b_hi && b < a.n2; b += blockDim.x) {
+        const long long newest_m = a.first_a2 + 4 * b;
+        const long long newest_d = a.first_a1 + 2 * newest_m;
+        if (newest_d < u0) continue;  // owned by the CTA before this one
+        const int pos = (int)(newest_m - m_lo);
+        float acc = 0.0f;
+        for (int t = 0; t < a.a2_taps; t++) acc = mac<EXACT>(acc, s_t2[t], s_a1[pos - t]);
+        a.audio[b] = acc;
+    }
+}
+
+// Slides the delay lines of the user filter and of both decimators in one launch (FirFilter keeps the newest
+// taps-1 inputs): new = last `hist` samples of (old history ++ this call's `n` inputs).
+__global__ void chain_state_kernel(const ChainStateArgs a) {
+    const int which = blockIdx.x;  // 0: user filter (complex), 1: first decimator, 2: second decimator
+    const ChainStateArgs::Line &l = a.line[which];
+    for (int h = threadIdx.x; h < l.hist; h += blockDim.x) {
+        const long long k = l.n - l.hist + h;  // stream index relative to this call's first input
+        float r = 0.0f, q = 0.0f;
+        if (k >= 0) {
+            r = l.in_re[k];
+            if (l.in_im) q = l.in_im[k];
+        } else if (k + l.hist >= 0) {
+            r = l.old_re[k + l.hist];
+            if (l.old_im) q = l.old_im[k + l.hist];
+        }
+        l.new_re[h] = r;
+        if (l.new_im) l.new_im[h] = q;
+    }
+}
+
+}  // namespace
+
+cudaError_t fm_tail_launch(const FmTailArgs &a, bool exact, cudaStream_t st) {
+    if (a.nu <= 0) return cudaSuccess;
+    if (a.user_taps > UT || a.user_taps < 1 || a.a1_taps > 9 || a.a2_taps > 13) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)((a.nu + TILE - 1) / TILE);
+    if (exact)
+        fm_tail_kernel<true><<<grid, 256, 0, st>>>(a);
+    else
+        fm_tail_kernel<false><<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t chain_state_launch(const ChainStateArgs &a, cudaStream_t st) {
+    chain_state_kernel<<<3, 64, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace rfa

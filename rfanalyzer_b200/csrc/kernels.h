@@ -34,6 +34,37 @@ cudaError_t demod_power_launch(const float *re, const float *im, long long n, fl
 cudaError_t agc_launch(float *x, const long long *off, int npackets, long long max_packet, bool subtract_mean,
                        float *state, float *scratch, float volume, bool exact, int num_sms, cudaStream_t st);
 
+// everything behind the resampler of an FM chain in one launch (chain_fused.cu)
+struct FmTailArgs {
+    const float *q_re, *q_im;              // quadrature samples of this call (resampler output)
+    const float *hist_u_re, *hist_u_im;    // user filter delay line (user_hist samples before index 0)
+    int user_hist, user_taps;
+    const float *taps_user;
+    long long first_u;                     // newest input index of user output 0 (decimationCounter, FirFilter.kt:46)
+    long long nu;                          // user filter outputs = demodulator samples of this call
+    const float *carry_in;                 // [2] last filtered sample of the previous call
+    float *carry_out;                      // [2]
+    float gain, volume;
+    int ratio;                             // demodulated rate / 48 kHz: 1 (no decimator), 2 (first only), 8 (both)
+    const float *taps_a1, *taps_a2;
+    int a1_taps, a2_taps, a1_hist, a2_hist;
+    const float *hist_a1, *hist_a2;        // delay lines of the decimators (demodulated / first-decimator samples)
+    long long first_a1, first_a2, n1, n2;
+    float *dem_out, *a1_out;               // intermediates kept for the next call's delay lines (may be NULL when unused)
+    float *audio;                          // 48 kHz audio of this call
+};
+cudaError_t fm_tail_launch(const FmTailArgs &a, bool exact, cudaStream_t st);
+// the delay lines of the user filter and both decimators slide in one launch
+struct ChainStateArgs {
+    struct Line {
+        const float *in_re, *in_im, *old_re, *old_im;
+        float *new_re, *new_im;
+        long long n;  // inputs of this call
+        int hist;     // 0 = unused
+    } line[3];
+};
+cudaError_t chain_state_launch(const ChainStateArgs &a, cudaStream_t st);
+
 // waterfall / trace preprocessing (render.cu); viewport scalars are computed by the caller (capi.cu)
 struct RenderDesc {
     const float *rows = nullptr;
