@@ -25,11 +25,11 @@ __device__ __forceinline__ float mac(float acc, float a, float b) {
     return EXACT ? __fadd_rn(acc, __fmul_rn(a, b)) : fmaf(a, b, acc);
 }
 
-constexpr int TILE = 2048;     // demodulator samples owned by a CTA
+// TILE = demodulator samples owned by a CTA: 2048, or 512 when the call is too short to fill the machine with those
 constexpr int HALO = 40;       // >= 1 (discriminator) + 8 (first decimator) + 2 * 12 (second) demodulator samples before the run
 constexpr int UT = 32;         // user filter taps at most (27 in the reference)
 
-template <bool EXACT>
+template <bool EXACT, int TILE>
 __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
     __shared__ float s_qre[TILE + HALO + UT], s_qim[TILE + HALO + UT];  // quadrature samples (user filter input)
     __shared__ float s_ure[TILE + HALO], s_uim[TILE + HALO];            // user filter output
@@ -179,11 +179,19 @@ __global__ void chain_state_kernel(const ChainStateArgs a) {
 cudaError_t fm_tail_launch(const FmTailArgs &a, bool exact, cudaStream_t st) {
     if (a.nu <= 0) return cudaSuccess;
     if (a.user_taps > UT || a.user_taps < 1 || a.a1_taps > 9 || a.a2_taps > 13) return cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)((a.nu + TILE - 1) / TILE);
-    if (exact)
-        fm_tail_kernel<true><<<grid, 256, 0, st>>>(a);
-    else
-        fm_tail_kernel<false><<<grid, 256, 0, st>>>(a);
+    if (a.nu >= 2048LL * 512) {
+        const unsigned grid = (unsigned)((a.nu + 2047) / 2048);
+        if (exact)
+            fm_tail_kernel<true, 2048><<<grid, 256, 0, st>>>(a);
+        else
+            fm_tail_kernel<false, 2048><<<grid, 256, 0, st>>>(a);
+    } else {
+        const unsigned grid = (unsigned)((a.nu + 511) / 512);
+        if (exact)
+            fm_tail_kernel<true, 512><<<grid, 256, 0, st>>>(a);
+        else
+            fm_tail_kernel<false, 512><<<grid, 256, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -23,6 +23,7 @@
 #include "device_once.h"
 #include "kernels.h"
 #include "rfa_fft_core.cuh"
+#include "spectrum_kernel.cuh"  // decode_point: magic-number sample conversion
 
 namespace rfa {
 namespace {
@@ -371,6 +372,307 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiled
     }
 }
 
+
+// Staging for the hot case of the stripe kernel: integer IQ, the whole span inside this call's input (k_al >= 0), NCO
+// table in shared memory as (cos, sin) pairs.  A thread takes two consecutive samples per round -- one 64-bit (int16)
+// or 32-bit (8-bit IQ) load, magic-number conversion without I2F (rfa_fft_core.cuh decode_point), three packed FP32
+// instructions for the mixer (products rounded separately like the reference's tables, then -/+), one 128-bit
+// conflict-free store -- about a dozen instructions per sample where stage_span spends sixty.
+// `raw_s` != nullptr: the raw codes of the span already sit in shared memory (bulk copy), nothing waits on DRAM here.
+template <int KIND>
+__device__ __forceinline__ void stage_span_pairs(const StreamSrc &src, long long k_al, int span, float2 *xs, const float2 *s_nco,
+                                                 int t_first /* NCO index of sample k_al */, const void *raw_s = nullptr) {
+    const int nco_len = src.nco_len > 0 ? src.nco_len : 1;
+    const int npairs = span >> 1;  // an odd last sample is left to the caller
+    int t = (t_first + 2 * (int)threadIdx.x) % nco_len;
+    const int tstep = (2 * (int)blockDim.x) % nco_len;
+    const bool mixing = src.nco_cos != nullptr;
+    constexpr float unit = KIND == FMT_S16LE ? (1.0f / 32768.0f) : 0.0078125f;
+    constexpr int U = 8;  // loads in flight per thread: a chain of DRAM round trips otherwise
+    for (int pr0 = threadIdx.x; pr0 < npairs; pr0 += U * blockDim.x) {
+        uint32_t r0[U], r1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int pr = pr0 + u * (int)blockDim.x;
+            r0[u] = r1[u] = 0u;
+            if (pr < npairs) {
+                if (KIND == FMT_S16LE) {
+                    const uint2 v = raw_s ? reinterpret_cast<const uint2 *>(raw_s)[pr]
+                                          : __ldg(reinterpret_cast<const uint2 *>((const uint32_t *)src.raw + k_al) + pr);
+                    r0[u] = v.x;
+                    r1[u] = v.y;
+                } else {
+                    const uint32_t v = raw_s ? reinterpret_cast<const uint32_t *>(raw_s)[pr]
+                                             : __ldg(reinterpret_cast<const uint32_t *>((const uint16_t *)src.raw + k_al) + pr);
+                    r0[u] = v & 0xFFFFu;
+                    r1[u] = v >> 16;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int pr = pr0 + u * (int)blockDim.x;
+            cf a = decode_point<KIND>(r0[u], unit), b = decode_point<KIND>(r1[u], unit);
+            if (mixing) {
+                const int t1 = t + 1 == nco_len ? 0 : t + 1;
+                const float2 c0 = s_nco[t], c1 = s_nco[t1];
+                // re = r*c - q*s, im = q*c + r*s, every product rounded on its own (Signed8BitIQConverter.java:119-120)
+                const cf p0 = cscale(a, c0.x), q0 = cscale(cf{a.y, a.x}, c0.y);
+                a = cadd(p0, cf{-q0.x, q0.y});
+                const cf p1 = cscale(b, c1.x), q1 = cscale(cf{b.y, b.x}, c1.y);
+                b = cadd(p1, cf{-q1.x, q1.y});
+                t += tstep;
+                if (t >= nco_len) t -= nco_len;
+            }
+            if (pr < npairs) *reinterpret_cast<float4 *>(xs + 2 * pr) = make_float4(a.x, a.y, b.x, b.y);
+        }
+    }
+}
+
+// ---- K4 (+K2), stripe path for large decimation (RFA_SUM_FMA) -----------------------------------------------------
+// Airspy 10 Msps -> 96 kHz is I/D = 6/625 with 501 taps per phase: every input sample is used by 4.8 outputs, yet a
+// load pair per multiply-add (resample_fast_kernel) makes the shared-memory pipe, not the 64 MB of input, the bound.
+// Two facts of the polyphase structure give register reuse:
+//   * outputs j and j + I have the SAME phase (taps) and windows exactly D samples apart, so one tap serves TP
+//     periods:  acc[pi] += h * x[n + pi*D];
+//   * neighbouring phases of one period look at almost the same samples (windows ~D/I apart), so one sample serves
+//     PH phases:  acc[s] += h_s[P_s - n] * x[n]  (a tap index outside 0 .. nt-1 is a zero tap).
+// A warp owns PH phases x TP periods; its lanes stripe over the union of those windows (neighbouring lanes read
+// neighbouring samples and taps: conflict-free), each lane keeps PH*TP packed accumulators -- TP + PH loads per PH*TP
+// packed multiply-adds -- and the 32 partial sums per output meet through shared memory.  A CTA stages TPC periods of
+// decoded, NCO-mixed samples once (stage_span) and its warps share them.
+struct ResampleStripeArgs {
+    ResampleArgs a;  // a.tile = I * TPC outputs per CTA
+    int TPC;         // periods per CTA (a multiple of TP)
+    int pad;         // zero taps on either side of a bank row in shared memory
+    int raw_bytes;   // shared-memory room for the next tile's raw codes (0: no bulk-copy staging)
+    int acc_pairs;   // I * TPC rounded up to an even count: per-output accumulators in front of the samples
+    int nco_pairs;   // room for the (cos, sin) table
+};
+
+#ifdef RFA_STRIPE_TRACE
+__device__ unsigned long long g_stripe_trace[8];
+#define STRIPE_STAMP(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_stripe_trace[k], (unsigned long long)(now_ - t_prev_)); t_prev_ = now_; } } while (0)
+#else
+#define STRIPE_STAMP(k) do {} while (0)
+#endif
+template <int KIND, int PH, int TP, bool DODD>
+__global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStripeArgs sa) {
+#ifdef RFA_STRIPE_TRACE
+    long long t_prev_ = clock64();
+#endif
+    const ResampleArgs &a = sa.a;
+    // shared memory: [2 + span_max + 8] samples (two entries of slack in front: a lane may look one sample back), the
+    // NCO table [512], the bank as zero-padded rows [I][pad + nt + pad], reduction scratch, slot table
+    extern __shared__ float2 smem_stripe[];
+    float2 *xs = smem_stripe + sa.acc_pairs + 2;  // [acc_pairs] output accumulators first (16-byte multiple), then two entries of slack
+    float2 *s_nco = xs + a.span_max + 8;
+    float *sbank = reinterpret_cast<float *>(s_nco + sa.nco_pairs);
+    const int RS = a.nt + 2 * sa.pad;
+    int *s_slot = reinterpret_cast<int *>(sbank + (size_t)a.I * RS);  // [I][2]: newest-sample position, tap row
+    // raw IQ codes of the NEXT tile: one bulk copy (TMA) issued before this tile's dot products, landed when they end
+    unsigned char *s_raw = reinterpret_cast<unsigned char *>(s_slot + 2 * a.I + 2);
+    s_raw += (16 - ((size_t)s_raw & 15)) & 15;
+    __shared__ int s_t0;
+    __shared__ __align__(8) unsigned long long s_mbar;
+    constexpr int BPS = KIND == FMT_S16LE ? 4 : 2;
+    constexpr bool INTFMT = KIND == FMT_S8 || KIND == FMT_U8 || KIND == FMT_S16LE;
+    const bool tma_ok = INTFMT && sa.raw_bytes > 0 && ((size_t)a.src.raw & 15) == 0;
+    if (tma_ok && threadIdx.x == 0) mbar_init(&s_mbar);
+    unsigned int waits = 0;  // completed bulk copies so far (CTA-uniform): the mbarrier's phase parity
+    // geometry of a tile: first staged sample, samples, and how many of them a bulk copy may fetch
+    auto tile_geom = [&](long long tile, long long *k_al_out, int *span_out, int *tma_samples) {
+        const long long j0t = tile * a.tile;
+        const long long T0t = (long long)a.ph0 + j0t * a.D;
+        const long long k_first = a.rel + T0t / a.I;
+        long long k_hi = a.rel + (T0t + (long long)(a.I - 1) * a.D) / a.I + (long long)(sa.TPC - 1) * a.D;
+        const long long k_end = a.rel + ((long long)a.ph0 + (a.nout - 1) * a.D) / a.I;  // newest sample any output needs
+        if (k_hi > k_end) k_hi = k_end;  // last tile: never read past the input
+        const long long k_lo = k_first - (a.nt - 1);
+        constexpr int AL = 16 / BPS;  // a bulk copy starts on a 16-byte boundary of the input
+        const long long k_al = k_lo - (((k_lo % AL) + AL) % AL);
+        const int span = (int)(k_hi - k_al + 1);
+        *k_al_out = k_al;
+        *span_out = span;
+        // whole 16-byte units only (the copy must not run past the newest sample the call owns), whole pairs of samples
+        int ts = (tma_ok && k_al >= 0) ? (int)(((long long)span * BPS) & ~15LL) / BPS : 0;
+        if ((long long)ts * BPS > sa.raw_bytes) ts = 0;
+        *tma_samples = ts;
+    };
+    // once per CTA: the polyphase bank (zero taps around every row, so that the inner loop needs no range test) and
+    // the NCO table; every load is issued before the first one is consumed -- a load/store pair per iteration is a
+    // chain of L2 round trips.  Then the CTA walks tiles blockIdx.x, +gridDim.x, ...
+    {
+        const int nb = a.I * RS;
+        constexpr int UB = 8;
+        for (int i0 = threadIdx.x; i0 < nb; i0 += UB * blockDim.x) {
+            float v[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int i = i0 + u * (int)blockDim.x, row = i / RS, t = i - row * RS - sa.pad;
+                v[u] = (i < nb && t >= 0 && t < a.nt) ? __ldg(a.bank + (size_t)row * a.nt + t) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++)
+                if (i0 + u * (int)blockDim.x < nb) sbank[i0 + u * blockDim.x] = v[u];
+        }
+        if (a.src.nco_cos)
+            for (int i = threadIdx.x; i < a.src.nco_len; i += blockDim.x) s_nco[i] = make_float2(__ldg(a.src.nco_cos + i), __ldg(a.src.nco_sin + i));
+        if (threadIdx.x < 2) smem_stripe[sa.acc_pairs + threadIdx.x] = make_float2(0.0f, 0.0f);
+    }
+    const long long ntiles = (a.nout + a.tile - 1) / a.tile;
+    __syncthreads();  // mbarrier initialised
+    STRIPE_STAMP(0);  // prologue
+    if (threadIdx.x == 0 && (long long)blockIdx.x < ntiles) {  // the first tile's raw codes start moving right away
+        long long k0;
+        int sp0, ts0;
+        tile_geom(blockIdx.x, &k0, &sp0, &ts0);
+        if (ts0) tma_load_1d(s_raw, (const char *)a.src.raw + k0 * BPS, (uint32_t)(ts0 * BPS), &s_mbar);
+    }
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long j0 = tile * a.tile;
+    const long long T0 = (long long)a.ph0 + j0 * a.D;
+    long long k_al;
+    int span, tma_samples;
+    tile_geom(tile, &k_al, &span, &tma_samples);
+    __syncthreads();  // the previous tile's warps are done with xs, the slot table and the output accumulators
+    for (int i = threadIdx.x; i < sa.acc_pairs; i += blockDim.x) smem_stripe[i] = make_float2(0.0f, 0.0f);
+    if ((int)threadIdx.x < a.I) {  // the 64-bit divisions happen once per tile, not once per warp task
+        const long long T = T0 + (long long)threadIdx.x * a.D;
+        s_slot[2 * threadIdx.x] = (int)(a.rel + T / a.I - k_al);
+        s_slot[2 * threadIdx.x + 1] = (int)(T % a.I) * RS + sa.pad;
+    }
+    const bool fast = INTFMT && k_al >= 0 && ((size_t)a.src.raw & 7) == 0;
+    if (fast) {
+        if (threadIdx.x == 0) s_t0 = (int)(((long long)a.src.nco_idx + k_al) % (a.src.nco_len > 0 ? a.src.nco_len : 1));
+        __syncthreads();
+        STRIPE_STAMP(1);  // top-of-tile barriers and slot table
+        if (tma_samples) {  // decode out of the bulk copy, then the few samples it could not carry
+            mbar_wait(&s_mbar, waits & 1u);
+            waits++;
+            STRIPE_STAMP(2);  // wait for the bulk copy
+            stage_span_pairs<KIND>(a.src, k_al, tma_samples, xs, s_nco, s_t0, s_raw);
+            for (int i = tma_samples + threadIdx.x; i < span; i += blockDim.x) {
+                float r, q;
+                fetch<KIND>(a.src, k_al + i, r, q);
+                xs[i] = make_float2(r, q);
+            }
+        } else {
+            stage_span_pairs<KIND>(a.src, k_al, span, xs, s_nco, s_t0);
+            if ((span & 1) && threadIdx.x == 0) {
+                float r, q;
+                fetch<KIND>(a.src, k_al + span - 1, r, q);
+                xs[span - 1] = make_float2(r, q);
+            }
+        }
+    } else {
+        stage_span<KIND>(a.src, k_al, span, xs);
+    }
+    // samples past the input (periods of the last tile that no output uses): defined values, never NaN
+    for (int i = span + threadIdx.x; i < a.span_max + 8; i += blockDim.x) xs[i] = make_float2(0.0f, 0.0f);
+    STRIPE_STAMP(3);  // decode (thread 0's share)
+    __syncthreads();
+    STRIPE_STAMP(4);  // barrier after decode
+    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) {  // the raw buffer is free: fetch the next tile under the dot products
+        long long kn;
+        int spn, tsn;
+        tile_geom(tile + gridDim.x, &kn, &spn, &tsn);
+        if (tsn) tma_load_1d(s_raw, (const char *)a.src.raw + kn * BPS, (uint32_t)(tsn * BPS), &s_mbar);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int groups = (a.I + PH - 1) / PH, blocks = sa.TPC / TP;
+    static_assert(PH * TP * 2 <= 32, "one lane per reduced value");
+    // A task = PH phases x TP periods; when a tile has fewer tasks than the CTA has warps, the sample range of a task is
+    // split over `nsplit` warps and the partial sums meet in shared memory (s_acc, one float pair per output).
+    const int ntasks = groups * blocks;
+    const int nsplit = ntasks < nwarps ? nwarps / ntasks : 1;
+    float *s_acc = reinterpret_cast<float *>(smem_stripe);  // [2 * I * TPC] -- lives in front of xs (see the launcher)
+    for (int sub = warp; sub < ntasks * nsplit; sub += nwarps) {
+        const int task = sub / nsplit, part = sub - task * nsplit;
+        const int s0 = (task % groups) * PH, pi0 = (task / groups) * TP;
+        // per phase slot: position of its newest sample in xs (period pi0) and its (padded) tap row
+        int base[PH];
+        const float *tapb[PH];
+#pragma unroll
+        for (int s = 0; s < PH; s++) {
+            const int slot = s0 + s < a.I ? s0 + s : a.I - 1;  // a short last group repeats its last slot (not written)
+            base[s] = s_slot[2 * slot] + pi0 * a.D;
+            tapb[s] = sbank + s_slot[2 * slot + 1] + base[s];  // tap of sample n: tapb[s][-n], zero outside 0 .. nt-1
+        }
+        cf acc[PH][TP];
+#pragma unroll
+        for (int s = 0; s < PH; s++)
+#pragma unroll
+            for (int q = 0; q < TP; q++) acc[s][q] = cf{0.0f, 0.0f};
+        // A lane takes the sample PAIR (n, n+1), n even, of every period with one 128-bit load; where q*D is odd the
+        // aligned pair is (n-1, n) instead -- every sample of every window is still visited exactly once.
+        const int n_first = (base[0] - (a.nt - 1)) & ~1, n_last = base[PH - 1] + 1;
+        const int chunks = (n_last - n_first) / 64 + 1;              // 64 samples per warp step
+        const int c_lo = chunks * part / nsplit, c_hi = chunks * (part + 1) / nsplit;
+        const float2 *xq = xs;
+        for (int n = n_first + 64 * c_lo + 2 * lane; n < n_first + 64 * c_hi; n += 64) {
+            float hm[PH], h0[PH], h1[PH];
+#pragma unroll
+            for (int s = 0; s < PH; s++) {
+                h0[s] = tapb[s][-n];
+                h1[s] = tapb[s][-n - 1];
+                hm[s] = DODD ? tapb[s][-n + 1] : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                const bool odd = DODD && (q & 1);
+                const float4 v = *reinterpret_cast<const float4 *>(xq + n + q * a.D - (odd ? 1 : 0));
+                const cf xa = cf{v.x, v.y}, xb = cf{v.z, v.w};
+#pragma unroll
+                for (int s = 0; s < PH; s++) {
+                    acc[s][q] = caxpy(odd ? hm[s] : h0[s], xa, acc[s][q]);
+                    acc[s][q] = caxpy(odd ? h0[s] : h1[s], xb, acc[s][q]);
+                }
+            }
+        }
+        // 32 lanes x 32 values -> lane v holds the total of value v: at every step half of the values a lane still
+        // carries go to its partner (31 shuffles in all instead of 5 per value, no shared memory)
+        float vals[32];
+#pragma unroll
+        for (int s = 0; s < PH; s++)
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                vals[(s * TP + q) * 2] = acc[s][q].x;
+                vals[(s * TP + q) * 2 + 1] = acc[s][q].y;
+            }
+#pragma unroll
+        for (int v = PH * TP * 2; v < 32; v++) vals[v] = 0.0f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; i++) {
+                const float send = upper ? vals[i] : vals[i + off];
+                const float keep = upper ? vals[i + off] : vals[i];
+                vals[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+            }
+        }
+        if (lane < PH * TP * 2) {
+            const int v = lane;
+            const int s = (v >> 1) / TP, q = (v >> 1) % TP;
+            if (s0 + s < a.I) atomicAdd(&s_acc[(((pi0 + q) * a.I) + s0 + s) * 2 + (v & 1)], vals[0]);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * a.tile; i += blockDim.x) {  // tile outputs: period-major, phase slot, (re, im)
+        const long long j = j0 + (i >> 1);
+        if (j < a.nout) {
+            if (i & 1)
+                a.out_im[j] = s_acc[i];
+            else
+                a.out_re[j] = s_acc[i];
+        }
+    }
+    STRIPE_STAMP(5);  // dot products (warp 0's tasks)
+  }  // tiles
+}
+
 // ---- K5 ------------------------------------------------------------------------------------
 struct FirArgs {
     StreamSrc src;
@@ -489,6 +791,65 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
     const size_t smem = 2 * (size_t)kSpanMax * sizeof(float);
     const bool aligned = in.kind == 3 || ((size_t)in.raw & (in.kind == 2 ? 3 : 1)) == 0;  // one IQ pair per load
     const int A = (nt + D - 1) / D;
+    // stripe path (large decimation: many taps per output window, windows of a phase far apart)
+    if (!exact && aligned && nt >= 256 && 2 * D >= nt && I <= 16) {
+        constexpr int kSpanS = 11300;  // samples per CTA (90 KB) + their raw codes (45 KB): one persistent CTA per SM
+        constexpr int PH = 2, TP = 8;  // two phases x eight periods per warp task; twelve warps per CTA share the tasks' sample ranges
+        long long tpc = ((long long)kSpanS - nt - D - 24) / D;
+        tpc -= tpc % TP;
+        if (tpc >= TP) {
+            ResampleStripeArgs sa{};
+            sa.a = a;
+            sa.TPC = (int)tpc;
+            sa.pad = (int)(((long long)(PH - 1) * D + I - 1) / I) + 1 + 68;
+            sa.a.tile = (int)(tpc * I);
+            sa.a.span_max = (int)(tpc * D + nt + D + 24);
+            const int groups = (I + PH - 1) / PH, tasks = groups * (int)(tpc / TP);
+            (void)tasks;
+            // variant A (default): two persistent CTAs of eight warps per SM, raw IQ loaded by the threads;
+            // variant B (knob rs_span = 2): one CTA of twelve warps per SM, the next tile's raw IQ arrives by bulk copy
+            const bool variant_b = rs_span == 2;
+            const int warps = variant_b ? 12 : 8;
+            sa.acc_pairs = (int)((tpc * I + 1) & ~1LL);
+            sa.raw_bytes = (variant_b && in.kind <= 2) ? (int)(((size_t)sa.a.span_max * (in.kind == 2 ? 4 : 2) + 15) & ~(size_t)15) : 0;
+            sa.nco_pairs = in.nco_cos ? ((in.nco_len + 7) & ~7) : 8;
+            const size_t ssmem = ((size_t)sa.a.span_max + 10 + sa.nco_pairs + sa.acc_pairs) * sizeof(float2) + (size_t)I * (nt + 2 * sa.pad) * sizeof(float) +
+                                 (size_t)(2 * I + 2) * sizeof(int) + 16 + sa.raw_bytes;
+            if (ssmem <= (variant_b ? 200 : 113) * 1024) {
+                long long stiles = (nout + sa.a.tile - 1) / sa.a.tile;
+                int sms = 148;
+                {
+                    int dev = 0;
+                    cudaGetDevice(&dev);
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                }
+                const long long resident = variant_b ? sms : 2LL * sms;
+                const unsigned sgrid = (unsigned)(stiles < resident ? stiles : resident);  // persistent CTAs walk the tiles
+                static DeviceOnce sonce;
+                int sdev = 0;
+                const bool sfirst = sonce.pending(&sdev);
+                const int mx = 200 * 1024;
+                const bool dodd = (D & 1) != 0;
+#define RFA_STRIPE(KIND, DO)                                                                                                    \
+    do {                                                                                                                        \
+        if (sfirst) cudaFuncSetAttribute(resample_stripe_kernel<KIND, PH, TP, DO>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); \
+        if (launch_now && in.kind == KIND && dodd == DO)                                                                        \
+            resample_stripe_kernel<KIND, PH, TP, DO><<<sgrid, 32 * warps, ssmem, st>>>(sa);                                     \
+    } while (0)
+                if (in.kind < 0 || in.kind > 3) return cudaErrorInvalidValue;
+                for (int pass = sfirst ? 0 : 1; pass < 2; pass++) {
+                    const bool launch_now = pass == 1;
+                    RFA_STRIPE(0, false); RFA_STRIPE(0, true);
+                    RFA_STRIPE(1, false); RFA_STRIPE(1, true);
+                    RFA_STRIPE(2, false); RFA_STRIPE(2, true);
+                    RFA_STRIPE(3, false); RFA_STRIPE(3, true);
+                    if (pass == 0) sonce.done(sdev);
+                }
+#undef RFA_STRIPE
+                return cudaGetLastError();
+            }
+        }
+    }
     if (!exact && aligned && A >= 2 && A <= 12 && (size_t)I * D * 12 <= 8192) {
         // register-tiled path: M = 9 outputs per thread, B blocks per phase
         constexpr int M = 9, kSpanT = 4096;  // 4 K samples per CTA: six CTAs per SM overlap staging and dot products
@@ -693,3 +1054,13 @@ cudaError_t history_launch(const StreamDesc &in, long long consumed, float *new_
 }
 
 }  // namespace rfa
+
+#ifdef RFA_STRIPE_TRACE
+extern "C" int rfa_debug_stripe_trace(unsigned long long *out) {
+    cudaDeviceSynchronize();
+    unsigned long long z[8] = {0};
+    cudaMemcpyFromSymbol(out, rfa::g_stripe_trace, sizeof(z));
+    cudaMemcpyToSymbol(rfa::g_stripe_trace, z, sizeof(z));
+    return 0;
+}
+#endif

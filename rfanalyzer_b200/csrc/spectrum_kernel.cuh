@@ -214,6 +214,31 @@ struct SpectrumFrame {
 #pragma unroll
             for (int r = 1; r < R; r++) twreg[b * (R - 1) + r - 1] = t[(r - 1) * P + ((tid + b * T) & (P - 1))];
     }
+    // a middle pass with its twiddles fetched into registers by the caller (before the exchange barrier)
+    template <int PASS>
+    static RFA_HD void load_pass_tw(const cf *tw, int tid, cf *twreg) {
+        constexpr int R = PL::radix(PASS), P = PL::prod(PASS), NB = E / R;
+        const cf *t = tw + pass_tw_offset<NL>(PASS);
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int r = 1; r < R; r++) twreg[b * (R - 1) + r - 1] = t[(r - 1) * P + ((tid + b * T) & (P - 1))];
+    }
+    template <int PASS>
+    static RFA_HD void gather_reg(const cf *x, const cf *twreg, int tid, cf *u) {
+        constexpr int R = PL::radix(PASS), NB = E / R, STR = NL / R;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const cf *xi = x + phys(tid + b * T);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                cf v = xi[r * (STR + STR / 16)];
+                if (r > 0) v = cmul(v, twreg[b * (R - 1) + r - 1]);
+                u[b * R + r] = v;
+            }
+            Dft<R>::run(u + b * R);
+        }
+    }
     static RFA_HD void gather_last_reg(const cf *x, const cf *twreg, int tid, cf *u) {
         constexpr int R = PL::radix(LAST), NB = E / R, STR = NL / R;
 #pragma unroll
@@ -376,8 +401,18 @@ struct MiddlePasses {
         using F = SpectrumFrame<NL, S, IN, OUT>;
         if constexpr (PASS < Plan<NL>::PASSES) {
             cf *x = ((PASS - 1) & 1) ? x1 : x0;
+#ifdef RFA_TWPRE
+            // twiddles of a middle pass are fetched BEFORE the exchange barrier (their addresses do not depend on the
+            // exchange, and the 32 registers of u[] are dead between scatter and gather): the loads fly while the CTA waits
+            constexpr bool PRE = PASS != F::LAST && F::MID_TW_SMEM && (Geom<NL>::E / Plan<NL>::radix(PASS)) * (Plan<NL>::radix(PASS) - 1) <= 16;
+            cf twpre[PRE ? (Geom<NL>::E / Plan<NL>::radix(PASS)) * (Plan<NL>::radix(PASS) - 1) : 1];
+#else
+            constexpr bool PRE = false;
+            cf twpre[1];
+#endif
 #ifndef RFA_EXP_NOXCHG
             F::template scatter<PASS - 1>(x, tid, u);
+            if constexpr (PRE) F::template load_pass_tw<PASS>(tw_mid, tid, twpre);
             RFA_STAMP(tbase + 2 * PASS - 1);  // scatter issued
             __syncthreads();
             RFA_STAMP(tbase + 2 * PASS);      // barrier passed
@@ -387,6 +422,8 @@ struct MiddlePasses {
                 F::gather_last_reg(x, twreg, tid, u);
             else if constexpr (PASS == F::LAST)
                 F::template gather<PASS>(x, tw_all, tid, u);
+            else if constexpr (PRE)
+                F::template gather_reg<PASS>(x, twpre, tid, u);
             else
                 F::template gather<PASS>(x, tw_mid, tid, u);
             if constexpr (Geom<NL>::NBUF == 1 && PASS + 1 < Plan<NL>::PASSES) __syncthreads();
