@@ -67,12 +67,22 @@ int rfa_ctx::use() {
     return RFA_OK;
 }
 
+static const int kColumnTwiddles = 1 << 24;
+
 int rfa_ctx::get_twiddles(int n, const cf **out) {
     auto it = twiddles.find(n);
     if (it == twiddles.end()) {
-        // n > 0: per-pass Stockham tables of an n-point transform; n < 0: plain exp(-2*pi*i*t/|n|)
+        // n > 0: per-pass Stockham tables of an n-point transform; n < 0: plain exp(-2*pi*i*t/|n|);
+        // n = kColumnTwiddles + N: the four-step column twiddles [N/256][256], W_N^(n2 k1) at row k1 (cluster path)
         std::vector<cf> host;
-        if (n > 0) {
+        if (n > kColumnTwiddles) {
+            const int N = n - kColumnTwiddles, n1 = N / 256;
+            std::vector<cf> w((size_t)N);
+            make_twiddles(N, w.data());
+            host.resize((size_t)N);
+            for (int k1 = 0; k1 < n1; k1++)
+                for (int n2 = 0; n2 < 256; n2++) host[(size_t)k1 * 256 + n2] = w[(size_t)(n2 * k1) & (size_t)(N - 1)];
+        } else if (n > 0) {
             host = make_pass_twiddles(n);
         } else {
             host.resize((size_t)-n);
@@ -486,6 +496,14 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
         if (int rc = c->get_twiddles(n / 256, &fs.tw_n1)) return rc;
         if (int rc = c->get_twiddles(256, &fs.tw_256)) return rc;
         fs.tw_n = pl->twN;
+        // first choice: thread-block clusters, the intermediate in distributed shared memory (one launch, no Z buffer)
+        cudaError_t e4 = cudaErrorNotSupported;
+        if (c->tune.cluster) {
+            if (int rc = c->get_twiddles(kColumnTwiddles + n, &fs.tz)) return rc;
+            e4 = fourstep_cluster_launch(L, fs);
+            if (e4 == cudaSuccess) c->launches += fourstep_launches(n, nframes, 0);
+        }
+        if (e4 == cudaErrorNotSupported) {
         long long want = c->tune.fs_batch_kib << 10;  // knob "fs_batch_kib"; default: 128 MiB per batch
         const long long all = nframes * (long long)n * (long long)sizeof(cf);
         if (want > all) want = all;
@@ -495,9 +513,10 @@ static int spectrum_device(rfa_spectrum_plan *pl, const void *iq, long long nfra
         fs.sync = pl->fsync.as<unsigned int>();
         fs.z = pl->zbuf.as<cf>();
         fs.z_bytes = want;
-        cudaError_t e4 = fourstep_launch(L, fs);
+        e4 = fourstep_launch(L, fs);
+        if (e4 == cudaSuccess) c->launches += fourstep_launches(n, nframes, fs.z_bytes);
+        }
         if (e4 != cudaSuccess) return cuda_fail(e4, "four-step spectrum kernels");
-        c->launches += fourstep_launches(n, nframes, fs.z_bytes);
         if (aq.avg && !ema) {
             average_rows(rows, L.p.avg_newest, L.p.avg_dir, ring_rows, row_stride, aq.valid, pl->d.avg_len, n, aq.avg, c->stream);
             RFA_CK(cudaGetLastError());

@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "fourstep_cluster.cuh"
 #include "fourstep_kernel.cuh"
 #include "spectrum_launch.h"
 
@@ -213,6 +214,69 @@ cudaError_t run(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     return cudaSuccess;
 }
 
+// ---- cluster path (fourstep_cluster.cuh): one launch per call, Z in distributed shared memory ----
+template <int N1, int IN>
+cudaError_t run_cluster(const SpectrumLaunch &L, const FourStepLaunch &fs) {
+    using C = ClusterFS<N1, IN>;
+    constexpr int BPS = in_elem_bytes<IN>();
+    if (!L.tune.cluster || !fs.tz || L.p.nframes > 0x7FFFFFFFLL) return cudaErrorNotSupported;
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    Tuning tma_on = L.tune;
+    tma_on.fs_tma = 1;  // the cluster kernel has no per-thread load path
+    if (!make_input_map<N1>(L.p.in, L.p.nframes, BPS, &tmap, tma_on)) return cudaErrorNotSupported;
+    auto kc = fourstep_cluster_kernel<N1, IN>;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = L.stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static thread_local int dev_done = -1, max_clusters = 0;  // per instantiation <N1, IN>
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev_done != dev) {
+        max_clusters = 0;
+        if (cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) == cudaSuccess) {
+            cfg.gridDim = dim3((unsigned)(C::CS * L.num_sms));
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, kc, &cfg) != cudaSuccess) max_clusters = 0;
+        }
+        (void)cudaGetLastError();  // a device without room for this kernel takes the two-kernel path
+        dev_done = dev;
+    }
+    if (max_clusters < 1) return cudaErrorNotSupported;
+    long long clusters = max_clusters;
+    if (L.max_grid > 0 && clusters > L.max_grid / C::CS) clusters = L.max_grid / C::CS > 0 ? L.max_grid / C::CS : 1;
+    if (clusters > L.p.nframes) clusters = L.p.nframes;
+    FourStepParams a{};
+    a.p = L.p;
+    a.tw_n1 = fs.tw_n1;
+    a.tw_256 = fs.tw_256;
+    a.tz = fs.tz;
+    a.frame0 = 0;
+    a.nbatch = (int)L.p.nframes;
+    cfg.gridDim = dim3((unsigned)(clusters * C::CS));
+    e = cudaLaunchKernelEx(&cfg, kc, a, tmap);
+    if (e == cudaSuccess) g_last_launches = 1;
+    return e;
+}
+
+template <int N1>
+cudaError_t run_cluster_fmt(const SpectrumLaunch &L, const FourStepLaunch &fs) {
+    switch (L.in_fmt) {
+        case FMT_S8: return run_cluster<N1, FMT_S8>(L, fs);
+        case FMT_U8: return run_cluster<N1, FMT_U8>(L, fs);
+        case FMT_S16LE: return run_cluster<N1, FMT_S16LE>(L, fs);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <int N1>
 cudaError_t run_fmt(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     switch (L.in_fmt) {
@@ -235,6 +299,11 @@ bool fourstep_supported(int N, int in_fmt, int out_kind, const Tuning &tune) {
 }
 
 int fourstep_launches(int, long long, long long) { return g_last_launches; }
+
+cudaError_t fourstep_cluster_launch(const SpectrumLaunch &L, const FourStepLaunch &fs) {
+    if (L.p.nframes <= 0) return cudaSuccess;
+    return L.N == 65536 ? run_cluster_fmt<256>(L, fs) : run_cluster_fmt<128>(L, fs);
+}
 
 cudaError_t fourstep_launch(const SpectrumLaunch &L, const FourStepLaunch &fs) {
     if (L.p.nframes <= 0) return cudaSuccess;

@@ -30,6 +30,7 @@ struct FourStepParams {
     const cf *tw_n1;       // per-pass Stockham twiddles of an N1-point transform (make_pass_twiddles(N1))
     const cf *tw_256;      // ... of a 256-point transform
     const cf *tw_n;        // exp(-2*pi*i*t/N), t < N
+    const cf *tz;          // cluster path: [N1][256] column twiddles W_N^(n2 k1), row k1 (fourstep_cluster.cuh)
     cf *z;                 // [batch][N1][256]
     long long frame0;      // first frame of this batch
     int nbatch;            // frames in this batch

@@ -34,6 +34,7 @@ struct FourStepLaunch {
     const cf *tw_n1;    // make_pass_twiddles(N / 256)
     const cf *tw_256;   // make_pass_twiddles(256)
     const cf *tw_n;     // make_twiddles(N)
+    const cf *tz;       // [N / 256][256] column twiddles W_N^(n2 k1) of the cluster path
     cf *z;              // batch buffer
     long long z_bytes;
     unsigned int *sync;  // 2 * nframes counters for the fused launch (NULL: two kernels per batch)
@@ -41,6 +42,10 @@ struct FourStepLaunch {
 bool fourstep_supported(int N, int in_fmt, int out_kind, const Tuning &tune);
 int fourstep_launches(int N, long long nframes, long long z_bytes);  // of the most recent fourstep_launch on this thread
 cudaError_t fourstep_launch(const SpectrumLaunch &L, const FourStepLaunch &fs);
+// the same transform on thread-block clusters, the intermediate in distributed shared memory (fourstep_cluster.cuh): needs
+// fs.tw_n1, fs.tw_256, fs.tz only.  cudaErrorNotSupported: this call cannot take that path (knob "cluster" = 0, unaligned
+// input, no room for a cluster on the device) and the caller runs fourstep_launch instead.
+cudaError_t fourstep_cluster_launch(const SpectrumLaunch &L, const FourStepLaunch &fs);
 
 // small helper kernels (spectrum.cu)
 void fill_f32(float *dst, size_t n, float v, cudaStream_t s);

@@ -34,7 +34,7 @@ def emu():
     src = os.path.join(ROOT, "tests", "emu", "emu_spectrum.cpp")
     so = os.path.join(ROOT, "tests", "emu", "libemu_spectrum.so")
     deps = [src] + [os.path.join(ROOT, "rfanalyzer_b200", "csrc", f)
-                    for f in ("rfa_fft_core.cuh", "spectrum_kernel.cuh", "spectrum2_kernel.cuh", "spectrum64_kernel.cuh", "fourstep_kernel.cuh", "rfa_tables.h")]
+                    for f in ("rfa_fft_core.cuh", "spectrum_kernel.cuh", "spectrum2_kernel.cuh", "spectrum64_kernel.cuh", "fourstep_kernel.cuh", "fourstep_cluster.cuh", "rfa_tables.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
     lib = C.CDLL(so)
@@ -48,6 +48,8 @@ def emu():
     lib.emu_spectrum64.restype = C.c_int
     lib.emu_fourstep_spectrum.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong]
     lib.emu_fourstep_spectrum.restype = C.c_int
+    lib.emu_cluster_spectrum.argtypes = lib.emu_fourstep_spectrum.argtypes
+    lib.emu_cluster_spectrum.restype = C.c_int
     return lib
 
 

@@ -14,6 +14,7 @@
 #include "../../rfanalyzer_b200/csrc/spectrum2_kernel.cuh"
 #include "../../rfanalyzer_b200/csrc/spectrum64_kernel.cuh"
 #include "../../rfanalyzer_b200/csrc/fourstep_kernel.cuh"
+#include "../../rfanalyzer_b200/csrc/fourstep_cluster.cuh"
 
 using namespace rfa;
 
@@ -310,6 +311,96 @@ extern "C" int emu_fourstep_spectrum(int N, int in_fmt, int window_kind, const v
                                      float *peaks, long long store_from) {
     if (N == 65536) return emu_fourstep_fmt<256>(in_fmt, in, window_kind, nframes, rows, peaks, store_from);
     if (N == 32768) return emu_fourstep_fmt<128>(in_fmt, in, window_kind, nframes, rows, peaks, store_from);
+    return -1;
+}
+
+// ---- cluster path (fourstep_cluster.cuh): CS CTAs, each with its own Z tile; thread by thread, unit by unit ----
+template <int N1, int IN>
+int emu_cluster(const void *in, int window_kind, long long nframes, float *rows, float *peaks, long long store_from) {
+    using C = ClusterFS<N1, IN>;
+    using FA = FourStepA<N1, IN>;
+    constexpr int N = C::N, CS = C::CS, CPC = C::CPC, BPS = C::BPS;
+    std::vector<cf> tw1 = make_pass_twiddles(N1), tw256 = make_pass_twiddles(256), twN(N), tz((size_t)N);
+    make_twiddles(N, twN.data());
+    for (int k1 = 0; k1 < N1; k1++)
+        for (int n2 = 0; n2 < 256; n2++) tz[(size_t)k1 * 256 + n2] = twN[(size_t)(n2 * k1) & (size_t)(N - 1)];
+    std::vector<float> win;
+    if (window_kind >= 0) {
+        win.resize(N);
+        make_window(window_kind, N, win.data());
+    }
+    const float bias = -3.0102999566398120f * log2f((float)N);
+    std::vector<std::vector<cf>> Z(CS, std::vector<cf>((size_t)C::ROWS * 256));
+    std::vector<cf> xch(4096);
+    std::vector<unsigned char> tile((size_t)C::TILE_BYTES);
+    std::vector<std::array<cf, 16>> U(256);
+    std::vector<std::array<float, 16>> PK((size_t)CS * C::UNITS * 256);  // [rank][g][tid]
+    for (auto &a : PK) a.fill(-999999.0f);
+    for (long long f = 0; f < nframes; f++) {
+        const unsigned char *frame = (const unsigned char *)in + f * (long long)N * BPS;
+        for (int rank = 0; rank < CS; rank++)
+            for (int g = 0; g < C::UNITS; g++) {
+                const int c0 = rank * C::COLS + g * CPC;
+                for (int r = 0; r < N1; r++)  // the tensor-map box: N1 rows of CPC pairs
+                    memcpy(tile.data() + (size_t)r * CPC * BPS, frame + ((size_t)r * 256 + c0) * BPS, (size_t)CPC * BPS);
+                for (int tid = 0; tid < 256; tid++) {
+                    const int col = tid % CPC, t = tid / CPC;
+                    float wreg[16];
+                    uint32_t raw[16];
+                    FA::load_window(win.empty() ? nullptr : win.data(), c0 + col, t, wreg);
+                    FA::load_raw_tile(tile.data(), col, t, raw);
+                    FA::first(raw, wreg, U[tid].data());
+                    C::a_scatter(xch.data(), col, t, U[tid].data());
+                }
+                for (int tid = 0; tid < 256; tid++) {
+                    const int col = tid % CPC, t = tid / CPC, n2 = c0 + col;
+                    cf twz[16], u[16];
+                    C::load_col_tw(tz.data(), n2, t, twz);
+                    C::a_second(xch.data(), tw1.data(), twz, col, t, u,
+                                [&](int owner, int lrow, cf v) { Z[owner][(size_t)lrow * 256 + n2] = v; });
+                }
+            }
+        float *out = rows + f * (long long)N;
+        for (int rank = 0; rank < CS; rank++)
+            for (int g = 0; g < C::UNITS; g++) {
+                for (int tid = 0; tid < 256; tid++) {
+                    const int row1 = tid / 16, t1 = tid % 16;
+                    C::b_first(Z[rank].data() + (size_t)(16 * g + row1) * 256, t1, U[tid].data());
+                }
+                for (int tid = 0; tid < 256; tid++) C::b_scatter(xch.data(), tid / 16, tid % 16, U[tid].data());
+                for (int tid = 0; tid < 256; tid++) {
+                    const int row = tid % 16, tb = tid / 16, k1 = rank * C::ROWS + 16 * g + row;
+                    float *pk = PK[((size_t)rank * C::UNITS + g) * 256 + tid].data();
+                    if (f >= store_from)
+                        C::template b_second<true, true>(xch.data(), tw256.data(), row, tb, k1, out, pk, bias);
+                    else
+                        C::template b_second<true, false>(xch.data(), tw256.data(), row, tb, k1, out, pk, bias);
+                }
+            }
+    }
+    if (peaks)
+        for (int rank = 0; rank < CS; rank++)
+            for (int g = 0; g < C::UNITS; g++)
+                for (int tid = 0; tid < 256; tid++)
+                    for (int c = 0; c < 16; c++)
+                        peaks[C::bin_of(tid / 16, rank * C::ROWS + 16 * g + tid % 16, c)] = PK[((size_t)rank * C::UNITS + g) * 256 + tid][c];
+    return 0;
+}
+
+template <int N1>
+int emu_cluster_fmt(int in_fmt, const void *in, int window_kind, long long nframes, float *rows, float *peaks, long long store_from) {
+    switch (in_fmt) {
+        case FMT_S8: return emu_cluster<N1, FMT_S8>(in, window_kind, nframes, rows, peaks, store_from);
+        case FMT_U8: return emu_cluster<N1, FMT_U8>(in, window_kind, nframes, rows, peaks, store_from);
+        case FMT_S16LE: return emu_cluster<N1, FMT_S16LE>(in, window_kind, nframes, rows, peaks, store_from);
+    }
+    return -1;
+}
+
+extern "C" int emu_cluster_spectrum(int N, int in_fmt, int window_kind, const void *in, long long nframes, float *rows,
+                                    float *peaks, long long store_from) {
+    if (N == 65536) return emu_cluster_fmt<256>(in_fmt, in, window_kind, nframes, rows, peaks, store_from);
+    if (N == 32768) return emu_cluster_fmt<128>(in_fmt, in, window_kind, nframes, rows, peaks, store_from);
     return -1;
 }
 

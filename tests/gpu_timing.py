@@ -7,6 +7,8 @@ from oracle import oracle as O
 
 stream = torch.cuda.Stream()
 ctx = rfa.Context(0, stream)
+for kv in filter(None, os.environ.get("KNOBS", "").split(",")):  # e.g. KNOBS=cluster=0,pdl=0
+    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 reps, nbuf = 30, 6
 fmt = int(os.environ.get("FMT", "0"))
 sizes = [int(x) for x in os.environ.get("SIZES", "4096,1024,2048,8192,16384,32768,65536").split(",")]

@@ -159,3 +159,37 @@ def test_fourstep_store_from_keeps_older_rows_untouched(emu, oracle):
     assert np.all(rows[:2] == 7.0)
     assert np.abs(rows[2] - r[2]).max() < 0.01
     assert np.abs(peaks - p).max() < 0.01      # peak hold still sees every frame
+
+
+# ---- cluster path (fourstep_cluster.cuh): the same factorisation, the intermediate in the CTAs' shared memory ----
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_cluster_path_vs_oracle_and_two_kernel_path(emu, oracle, fmt, n):
+    """Ownership of columns / rows by cluster rank, the dense step-A exchange and the XOR-swizzled step-B exchange,
+    thread by thread; the butterflies are those of the two-kernel path, so the rows are identical bit for bit."""
+    frames = 2
+    iq = oracle.synth_iq(fmt, n * frames)
+    rows = np.full((frames, n), 7.0, np.float32)
+    peaks = np.zeros(n, np.float32)
+    assert emu.emu_cluster_spectrum(n, fmt, 0, iq.ctypes.data, frames, rows.ctypes.data, peaks.ctypes.data, 0) == 0
+    r, p, _ = oracle.spectrum_run(fmt, iq, n, 1)
+    assert np.abs(rows - r).max() < 0.01
+    assert np.abs(peaks - p).max() < 0.01
+    lin, lin_ref = 10.0 ** (rows / 5.0), 10.0 ** (r / 5.0)
+    assert np.all(np.abs(lin - lin_ref) <= 1e-4 * lin_ref + 1e-6 * lin_ref.max())
+    rows2 = np.zeros((frames, n), np.float32)
+    peaks2 = np.zeros(n, np.float32)
+    assert emu.emu_fourstep_spectrum(n, fmt, 0, iq.ctypes.data, frames, rows2.ctypes.data, peaks2.ctypes.data, 0) == 0
+    assert np.array_equal(rows, rows2) and np.array_equal(peaks, peaks2)
+
+
+def test_cluster_path_store_from(emu, oracle):
+    n, frames = 65536, 3
+    iq = oracle.synth_iq(2, n * frames)
+    rows = np.full((frames, n), 7.0, np.float32)
+    peaks = np.zeros(n, np.float32)
+    assert emu.emu_cluster_spectrum(n, 2, 0, iq.ctypes.data, frames, rows.ctypes.data, peaks.ctypes.data, 2) == 0
+    r, p, _ = oracle.spectrum_run(2, iq, n, 1)
+    assert np.all(rows[:2] == 7.0)
+    assert np.abs(rows[2] - r[2]).max() < 0.01
+    assert np.abs(peaks - p).max() < 0.01

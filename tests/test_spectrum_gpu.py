@@ -279,13 +279,17 @@ def parse_name(ctx, path):
 
 
 # ---- four-step path (fourstep_kernel.cuh), N = 32768 / 65536 ----
-@pytest.mark.parametrize("fmt,n,frames,batch_kib", [(0, 65536, 7, 1024), (2, 32768, 9, 512), (1, 65536, 3, 0)])
-def test_fourstep_batches_ring_and_history(gpu_ctx, oracle, monkeypatch, fmt, n, frames, batch_kib):
+@pytest.mark.parametrize("fmt,n,frames,batch_kib,cluster", [(0, 65536, 7, 1024, 0), (2, 32768, 9, 512, 0), (1, 65536, 3, 0, 0),
+                                                            (0, 65536, 7, 0, 1), (2, 32768, 9, 0, 1), (1, 32768, 3, 0, 1),
+                                                            (2, 65536, 5, 0, 1)])
+def test_fourstep_batches_ring_and_history(gpu_ctx, oracle, monkeypatch, fmt, n, frames, batch_kib, cluster):
     """Several batches through a small intermediate buffer (knob "fs_batch_kib"), rows into a
-    backwards ring with history, accumulating peaks, average over ring rows."""
+    backwards ring with history, accumulating peaks, average over ring rows -- through the two-kernel path
+    (knob "cluster" = 0) and through the cluster path (fourstep_cluster.cuh, the default)."""
     import torch
     import rfanalyzer_b200 as rfa
     L, ring = 4, 12
+    gpu_ctx.set_option("cluster", cluster)  # restored by the fixture
     if batch_kib:   # several batches through a small intermediate buffer (context knob, restored by the fixture below)
         gpu_ctx.set_option("fs_batch_kib", batch_kib)
     plan = rfa.SpectrumPlan(gpu_ctx, fmt, n, avg_len=L)
@@ -325,6 +329,7 @@ def test_fourstep_tensor_map_staging_equals_per_thread_loads(gpu_ctx, oracle, mo
     import rfanalyzer_b200 as rfa
     frames = 5
     iq = oracle.synth_iq(fmt, n * frames)
+    gpu_ctx.set_option("cluster", 0)  # the two-kernel path (restored by the fixture)
     rows_t, peaks_t, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
     with gpu_ctx.options(fs_tma=0):
         rows_l, peaks_l, _ = gpu_spectrum(gpu_ctx, fmt, iq, n, L=2)
@@ -343,13 +348,55 @@ def test_fourstep_tensor_map_staging_equals_per_thread_loads(gpu_ctx, oracle, mo
     assert np.array_equal(rows_m.cpu().numpy(), rows_t)
 
 
+@pytest.mark.parametrize("fmt,n", [(0, 65536), (1, 32768), (2, 65536), (2, 32768), (0, 32768)])
+def test_cluster_path_equals_the_two_kernel_path(gpu_ctx, oracle, fmt, n):
+    """N >= 32768 on thread-block clusters (the intermediate in distributed shared memory, ONE launch) against the
+    two-kernel path (the intermediate in HBM): the same butterflies in the same order, so identical bits.  More frames
+    than clusters, so that every cluster walks several frames and the split cluster barrier is exercised; an input
+    that is not 16-byte aligned must fall back to the two-kernel path by itself."""
+    import torch
+    import rfanalyzer_b200 as rfa
+    frames = 2 * 37 + 5 if n == 65536 else 2 * 74 + 3
+    iq = oracle.synth_iq(fmt, n * frames)
+    plan = rfa.SpectrumPlan(gpu_ctx, fmt, n)
+    out = {}
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        d = torch.from_numpy(iq).cuda()
+        for cluster in (1, 0):
+            gpu_ctx.set_option("cluster", cluster)
+            rows = torch.zeros((frames, n), dtype=torch.float32, device="cuda")
+            peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
+            l0 = gpu_ctx.launch_count
+            plan.process(d, frames, rows=rows)
+            launches = gpu_ctx.launch_count - l0
+            plan.process(d, frames, rows=None, peaks=peaks)
+            gpu_ctx.sync()
+            out[cluster] = (rows.cpu().numpy(), peaks.cpu().numpy(), launches)
+        assert out[1][2] == 1 and out[0][2] == 2      # the cluster path really ran: one launch instead of two
+        assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1])
+        r, p, _ = oracle.spectrum_run(fmt, iq[: 3 * n * rfa.BYTES_PER_SAMPLE[fmt]], n, 0)
+        assert np.abs(out[1][0][:3] - r).max() < DB_TOL and lin_ok(out[1][0][:3], r)
+        assert np.array_equal(out[1][1], out[1][0].max(axis=0))
+        gpu_ctx.set_option("cluster", 1)
+        buf = torch.zeros(len(iq.view(np.uint8)) + 4, dtype=torch.uint8, device="cuda")
+        buf[4:] = torch.from_numpy(iq.view(np.uint8)).cuda()
+        rows_m = torch.zeros((frames, n), dtype=torch.float32, device="cuda")
+        l0 = gpu_ctx.launch_count
+        plan.process(buf[4:], frames, rows=rows_m)
+        gpu_ctx.sync()
+        assert gpu_ctx.launch_count - l0 == 2
+    assert np.array_equal(rows_m.cpu().numpy(), out[1][0])
+
+
+@pytest.mark.parametrize("cluster", [1, 0])
 @pytest.mark.parametrize("n", [32768, 65536])
-def test_fourstep_no_rows_peak_only_and_host_buffers(gpu_ctx, oracle, n):
+def test_fourstep_no_rows_peak_only_and_host_buffers(gpu_ctx, oracle, n, cluster):
     """The four-step path behind every output mode of rfa_spectrum_process: no rows (only the newest L+1 rows are
     kept for the average), peaks only, average only, and host buffers (chunked H2D -> kernels -> D2H pipeline)."""
     import torch
     import rfanalyzer_b200 as rfa
     frames, L = 11, 3
+    gpu_ctx.set_option("cluster", cluster)  # restored by the fixture
     iq = oracle.synth_iq(0, n * frames)
     r, p, a = oracle.spectrum_run(0, iq, n, L)
     plan = rfa.SpectrumPlan(gpu_ctx, 0, n, avg_len=L)
