@@ -75,9 +75,12 @@ struct ClusterFS {
                 u[b * R1 + r] = v;
             }
             Dft<R1>::run(u + b * R1);
+        }
 #pragma unroll
-            for (int c = 0; c < R1; c++)  // k1 = i + 16*c: owner c / 4, local row i + 16*(c % 4)
-                put(c >> 2, i + 16 * (c & 3), cmul(u[b * R1 + Dft<R1>::perm(c)], twz[b * R1 + c]));
+        for (int c = 0; c < R1; c++) {  // k1 = i + 16*c: owner c / 4, local row i + 16*(c % 4)
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+                put(c >> 2, t + b * T1 + 16 * (c & 3), cmul(u[b * R1 + Dft<R1>::perm(c)], twz[b * R1 + c]));
         }
     }
 
@@ -131,8 +134,13 @@ __device__ __forceinline__ uint32_t map_shared_rank(uint32_t addr, uint32_t rank
 __device__ __forceinline__ void st_cluster(uint32_t addr, cf v) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
+#ifdef RFA_CL_NOBAR
+__device__ __forceinline__ void cluster_arrive() {}
+__device__ __forceinline__ void cluster_wait() {}
+#else
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+#endif
 __device__ __forceinline__ void team_barrier(int team) { asm volatile("bar.sync %0, 256;" ::"r"(team + 1) : "memory"); }
 
 // grid = clusters * CS CTAs of 512 threads, cluster dimension CS; cluster q transforms frames q, q + clusters, ...
@@ -184,6 +192,13 @@ __global__ void __launch_bounds__(512, 1) fourstep_cluster_kernel(const FourStep
 #pragma unroll
         for (int c = 0; c < 16; c++) pk[j][c] = -999999.0f;
     const bool want_peak = a.p.peaks != nullptr;
+    float wreg[16];  // window taps (times the format's unit) of the unit about to start
+#ifdef RFA_CL_NOWIN
+#pragma unroll
+    for (int r = 0; r < 16; r++) wreg[r] = 0.001f * (float)col;
+#else
+    FA::load_window(a.p.win, rank * C::COLS + team * CPC + col, t, wreg);
+#endif
     int it = 0;
     for (long long fb = cluster; fb < a.nbatch; fb += clusters, it++) {
         // ---- step A: two column groups per team ----
@@ -192,25 +207,39 @@ __global__ void __launch_bounds__(512, 1) fourstep_cluster_kernel(const FourStep
             const int g = 2 * j + team, n2 = rank * C::COLS + g * CPC + col, seq = 2 * it + j;
             cf u[16];
             {
-                float wreg[16];
                 uint32_t raw[16];
-                FA::load_window(a.p.win, n2, t, wreg);
                 mbar_wait(&s_mbar[team][seq % NT], (uint32_t)((seq / NT) & 1));
                 FA::load_raw_tile(tiles + (seq % NT) * C::TILE_BYTES, col, t, raw);
                 FA::first(raw, wreg, u);
             }
+            // the column twiddles travel from L2 while the exchange runs
+            cf twz[16];
+#ifdef RFA_CL_NOTWZ
+#pragma unroll
+            for (int e = 0; e < 16; e++) twz[e] = cf{0.5f, 0.001f * (float)n2};
+#else
+            C::load_col_tw(a.tz, n2, t, twz);
+#endif
             team_barrier(team);  // the tile is consumed, the previous unit is done with the exchange buffer
             if (tid == 0) fetch(seq + NT);
             C::a_scatter(xch, col, t, u);
-            cf twz[16];
-            C::load_col_tw(a.tz, n2, t, twz);
             team_barrier(team);
             if (j == 0 && it > 0) cluster_wait();  // every CTA has read the previous frame out of its Z tile
             const uint32_t zoff = (uint32_t)((t * 256 + n2) * sizeof(cf));
-            C::a_second(xch, tw1, twz, col, t, u, [&](int owner, int lrow, cf v) {
+            auto put = [&](int owner, int lrow, cf v) {
                 // lrow = i + 16*(c % 4) with i = t + b*T1: the part that depends on t sits in zoff
+#ifdef RFA_CL_LOCAL
+                zloc[(size_t)lrow * 256 + n2] = v;
+#else
                 st_cluster(zpeer[owner] + zoff + (uint32_t)((lrow - t) * 256 * sizeof(cf)), v);
-            });
+#endif
+            };
+            C::a_second(xch, tw1, twz, col, t, u, put);
+            // window taps of the team's NEXT column group (the other one): in flight across the rest of this unit's tail,
+            // and, after the frame's second unit, across step B
+#ifndef RFA_CL_NOWIN
+            FA::load_window(a.p.win, rank * C::COLS + (2 * (1 - j) + team) * CPC + col, t, wreg);
+#endif
         }
         cluster_arrive();  // my points of Z are written ...
         cluster_wait();    // ... and so are everybody else's

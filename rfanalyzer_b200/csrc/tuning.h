@@ -18,7 +18,11 @@ struct Tuning {
     int fs_pdl = 1;              // "fs_pdl": four-step kernels chained by programmatic dependent launch
     int chunk_kib = 4096;        // "chunk_kib": IQ bytes per chunk of the host-buffer H2D -> kernel -> D2H pipeline
     int rs_span = 0;             // "rs_span": samples staged per CTA by the tiled resampler, 0 = default
-    int cluster = 1;             // "cluster": N >= 32768 on thread-block clusters with distributed shared memory
+    // "cluster": N >= 32768 on thread-block clusters, the four-step intermediate in distributed shared memory
+    // (fourstep_cluster.cuh): ONE launch and a third of the two-kernel path's HBM traffic, but measured 119 / 93 us
+    // against 79 / 78 us per 2^24 samples (N = 65536 / 32768, profiles/r02d_cluster_experiments.txt) -- the remote
+    // stores and the per-frame table loads queue behind the same load/store unit -- so the two-kernel path is the default
+    int cluster = 0;
     // ---- lab builds only ----
     int kernel = 0;              // "kernel": 0 default, 1 dual-frame, 2 64x64, 3 anti-phase pair, 4 lean (N = 4096 variants)
     int fourstep = 1;            // "fourstep": 0 = residue-split kernel for N = 32768 / 65536 integer input

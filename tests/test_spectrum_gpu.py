@@ -20,7 +20,7 @@ def _default_knobs(request):
     yield
     if "gpu_ctx" in request.fixturenames:
         ctx = request.getfixturevalue("gpu_ctx")
-        for k, v in (("fs_batch_kib", 128 << 10), ("fs_tma", 1), ("fs_ztma", 1), ("staged", 1), ("pdl", 1), ("cluster", 1)):
+        for k, v in (("fs_batch_kib", 128 << 10), ("fs_tma", 1), ("fs_ztma", 1), ("staged", 1), ("pdl", 1), ("cluster", 0)):
             ctx.set_option(k, v)
 
 
@@ -285,7 +285,7 @@ def parse_name(ctx, path):
 def test_fourstep_batches_ring_and_history(gpu_ctx, oracle, monkeypatch, fmt, n, frames, batch_kib, cluster):
     """Several batches through a small intermediate buffer (knob "fs_batch_kib"), rows into a
     backwards ring with history, accumulating peaks, average over ring rows -- through the two-kernel path
-    (knob "cluster" = 0) and through the cluster path (fourstep_cluster.cuh, the default)."""
+    (knob "cluster" = 0, the default) and through the cluster path (fourstep_cluster.cuh, "cluster" = 1)."""
     import torch
     import rfanalyzer_b200 as rfa
     L, ring = 4, 12
@@ -377,7 +377,7 @@ def test_cluster_path_equals_the_two_kernel_path(gpu_ctx, oracle, fmt, n):
         r, p, _ = oracle.spectrum_run(fmt, iq[: 3 * n * rfa.BYTES_PER_SAMPLE[fmt]], n, 0)
         assert np.abs(out[1][0][:3] - r).max() < DB_TOL and lin_ok(out[1][0][:3], r)
         assert np.array_equal(out[1][1], out[1][0].max(axis=0))
-        gpu_ctx.set_option("cluster", 1)
+        gpu_ctx.set_option("cluster", 1)  # (restored by the fixture)
         buf = torch.zeros(len(iq.view(np.uint8)) + 4, dtype=torch.uint8, device="cuda")
         buf[4:] = torch.from_numpy(iq.view(np.uint8)).cuda()
         rows_m = torch.zeros((frames, n), dtype=torch.float32, device="cuda")
