@@ -31,22 +31,27 @@ constexpr int UT = 32;         // user filter taps at most (27 in the reference)
 
 template <bool EXACT, int TILE>
 __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
-    __shared__ float s_qre[TILE + HALO + UT], s_qim[TILE + HALO + UT];  // quadrature samples (user filter input)
+    // quadrature samples (user filter input) as (re, im) pairs; eight entries of slack in front: the last tap chunk of a
+    // thread's first outputs looks (never uses) a few entries before the first staged sample
+    __shared__ float2 s_q[8 + TILE + HALO + UT + 16];
     __shared__ float s_ure[TILE + HALO], s_uim[TILE + HALO];            // user filter output
     __shared__ float s_dem[TILE + HALO];                                // demodulated (index 0 = u0 - HALO + 1)
     __shared__ float s_a1[(TILE + HALO) / 2 + 2];                       // first decimator output
-    __shared__ float s_tu[UT], s_t1[16], s_t2[16];
+    __shared__ __align__(16) float s_tu[UT];
+    __shared__ float s_t1[16], s_t2[16];
     const long long u0 = (long long)blockIdx.x * TILE;                  // first demodulator index this CTA owns
     long long u1 = u0 + TILE;
     if (u1 > a.nu) u1 = a.nu;
     if (u0 >= u1) return;
-    for (int t = threadIdx.x; t < a.user_taps; t += blockDim.x) s_tu[t] = a.taps_user[t];
+    for (int t = threadIdx.x; t < UT; t += blockDim.x) s_tu[t] = t < a.user_taps ? a.taps_user[t] : 0.0f;
     if (threadIdx.x < a.a1_taps) s_t1[threadIdx.x] = a.taps_a1[threadIdx.x];
     if (threadIdx.x < a.a2_taps) s_t2[threadIdx.x] = a.taps_a2[threadIdx.x];
+    if (threadIdx.x < 8) s_q[threadIdx.x] = make_float2(0.0f, 0.0f);
     // ---- quadrature samples: user output i needs inputs first_u + i - (taps-1) .. first_u + i (decimation 1) ----
     const long long ulo = u0 - HALO;                                    // first user output computed here (may be < 0)
     const long long qlo = a.first_u + ulo - (a.user_taps - 1);
     const int nqs = (int)(u1 - ulo) + a.user_taps - 1;
+    float2 *xq = s_q + 8;
     for (int s = threadIdx.x; s < nqs; s += blockDim.x) {
         const long long k = qlo + s;
         float r = 0.0f, q = 0.0f;
@@ -57,27 +62,53 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
             r = a.hist_u_re[k + a.user_hist];
             q = a.hist_u_im[k + a.user_hist];
         }
-        s_qre[s] = r;
-        s_qim[s] = q;
+        xq[s] = make_float2(r, q);
     }
     __syncthreads();
     // ---- user filter (FirFilter.kt:90-96), outputs ulo .. u1-1; outputs with index < 0 belong to earlier calls ----
+    // A thread owns M consecutive outputs and walks the taps eight at a time, in the reference's order (t = 0 first):
+    // output s, tap t reads sample s + taps-1 - t, so a chunk of eight taps needs a window of M + 7 samples -- one
+    // 64-bit load per (re, im) pair and M * 8 multiply-adds per chunk instead of three loads per multiply-add pair.
     const int nus = (int)(u1 - ulo);
-    for (int s = threadIdx.x; s < nus; s += blockDim.x) {
-        float ar = 0.0f, ai = 0.0f;
-        if (ulo + s >= 0) {
-            const int pos = s + a.user_taps - 1;
-            for (int t = 0; t < a.user_taps; t++) {
-                const float h = s_tu[t];
-                ar = mac<EXACT>(ar, h, s_qre[pos - t]);
-                ai = mac<EXACT>(ai, h, s_qim[pos - t]);
+    constexpr int M = (TILE + HALO + 255) / 256;  // 9 (TILE 2048) / 3 (TILE 512): odd, so that lanes M samples apart hit distinct banks
+    static_assert(M % 2 == 1, "M must be odd");
+    for (int s0 = threadIdx.x * M; s0 < nus; s0 += blockDim.x * M) {
+        float ar[M], ai[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) ar[m] = ai[m] = 0.0f;
+        for (int t0 = 0; t0 < a.user_taps; t0 += 8) {
+            const float2 *xw = xq + (s0 + a.user_taps - 8 - t0);  // sample of (output s0, tap t0 + 7)
+            float2 w[M + 7];
+#pragma unroll
+            for (int i = 0; i < M + 7; i++) w[i] = xw[i];
+            const float4 ha = *reinterpret_cast<const float4 *>(s_tu + t0), hb = *reinterpret_cast<const float4 *>(s_tu + t0 + 4);
+            const float h[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (t0 + j < a.user_taps) {  // CTA-uniform
+#pragma unroll
+                    for (int m = 0; m < M; m++) {
+                        ar[m] = mac<EXACT>(ar[m], h[j], w[7 + m - j].x);
+                        ai[m] = mac<EXACT>(ai[m], h[j], w[7 + m - j].y);
+                    }
+                }
             }
-        } else if (ulo + s == -1) {  // the sample before this call's first one: the discriminator's carry
-            ar = a.carry_in[0];
-            ai = a.carry_in[1];
         }
-        s_ure[s] = ar;
-        s_uim[s] = ai;
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            const int sm = s0 + m;
+            if (sm < nus) {
+                float vr = ar[m], vi = ai[m];
+                if (ulo + sm == -1) {  // the sample before this call's first one: the discriminator's carry
+                    vr = a.carry_in[0];
+                    vi = a.carry_in[1];
+                } else if (ulo + sm < 0) {
+                    vr = vi = 0.0f;
+                }
+                s_ure[sm] = vr;
+                s_uim[sm] = vi;
+            }
+        }
     }
     __syncthreads();
     // ---- discriminator (Demodulator.kt:262-270) for demodulator indices ulo+1 .. u1-1 ----

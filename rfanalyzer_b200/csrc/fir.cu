@@ -226,6 +226,91 @@ __device__ __forceinline__ void stage_span(const StreamSrc &src, long long k_al,
         }
     }
 }
+// Staging for the hot case of the tiled and stripe kernels: integer IQ, the whole span inside this call's input
+// (k_al >= 0), NCO table in shared memory as (cos, sin) pairs PRE-SCALED by the format's power-of-two unit (scaling by a
+// power of two commutes with rounding: same bits) and with entry nco_len repeating entry 0 (the second sample of a pair
+// needs no wrap test).  A thread takes two consecutive samples per round -- one 64-bit (int16) or 32-bit (8-bit IQ)
+// load, magic-number conversion to the integer code without I2F, three packed FP32 instructions for the mixer, one
+// 128-bit conflict-free store -- about a dozen instructions per sample where stage_span spends sixty.
+// `raw_s` != nullptr: the raw codes of the span already sit in shared memory (bulk copy), nothing waits on DRAM here.
+template <int KIND>
+__device__ __forceinline__ cf decode_code(uint32_t raw) {  // the sample as (I, Q) in units of one code step
+    if (KIND == FMT_S8) {
+        raw ^= 0x8080u;
+        return cadd(cf{magic_byte0(raw), magic_byte1(raw)}, cf{-8388736.0f, -8388736.0f});
+    } else if (KIND == FMT_U8) {
+        return cadd(cadd(cf{magic_byte0(raw), magic_byte1(raw)}, cf{-8388608.0f, -8388608.0f}), cf{-127.4f, -127.4f});
+    } else {
+        raw ^= 0x80008000u;
+        return cadd(cf{magic_half0(raw), magic_half1(raw)}, cf{-8421376.0f, -8421376.0f});
+    }
+}
+template <int KIND>
+__device__ __forceinline__ void stage_span_pairs(const StreamSrc &src, long long k_al, int span, float2 *xs, const float2 *s_nco,
+                                                 int t_first /* NCO index of sample k_al */, const void *raw_s = nullptr) {
+    const int nco_len = src.nco_len > 0 ? src.nco_len : 1;
+    const int npairs = span >> 1;  // an odd last sample is left to the caller
+    int t = (t_first + 2 * (int)threadIdx.x) % nco_len;
+    const int tstep = (2 * (int)blockDim.x) % nco_len;
+    const bool mixing = src.nco_cos != nullptr;
+    constexpr float unit = KIND == FMT_S16LE ? (1.0f / 32768.0f) : 0.0078125f;
+    constexpr int U = 8;  // loads in flight per thread: a chain of DRAM round trips otherwise
+    for (int pr0 = threadIdx.x; pr0 < npairs; pr0 += U * blockDim.x) {
+        uint32_t r0[U], r1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int pr = pr0 + u * (int)blockDim.x;
+            r0[u] = r1[u] = 0u;
+            if (pr < npairs) {
+                if (KIND == FMT_S16LE) {
+                    const uint2 v = raw_s ? reinterpret_cast<const uint2 *>(raw_s)[pr]
+                                          : __ldg(reinterpret_cast<const uint2 *>((const uint32_t *)src.raw + k_al) + pr);
+                    r0[u] = v.x;
+                    r1[u] = v.y;
+                } else {
+                    const uint32_t v = raw_s ? reinterpret_cast<const uint32_t *>(raw_s)[pr]
+                                             : __ldg(reinterpret_cast<const uint32_t *>((const uint16_t *)src.raw + k_al) + pr);
+                    r0[u] = v & 0xFFFFu;
+                    r1[u] = v >> 16;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int pr = pr0 + u * (int)blockDim.x;
+            cf a = decode_code<KIND>(r0[u]), b = decode_code<KIND>(r1[u]);
+            if (mixing) {
+                const float2 c0 = s_nco[t], c1 = s_nco[t + 1];  // (cos, sin) * unit
+                // re = r*c - q*s, im = q*c + r*s, every product rounded on its own (Signed8BitIQConverter.java:119-120):
+                // the same bits as fetch<KIND> / stage_span produce, whichever tile or call a sample is staged in
+                // (packed products, SCALAR sums: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 in spite of the
+                // explicit rounding modifiers -- measured, build/dbg/stage_dbg.cu -- and only the scalar intrinsics are
+                // guaranteed to stay separate)
+                const cf p0 = cscale(a, c0.x), q0 = cscale(cf{a.y, a.x}, c0.y);
+                a = cf{__fsub_rn(p0.x, q0.x), __fadd_rn(p0.y, q0.y)};
+                const cf p1 = cscale(b, c1.x), q1 = cscale(cf{b.y, b.x}, c1.y);
+                b = cf{__fsub_rn(p1.x, q1.x), __fadd_rn(p1.y, q1.y)};
+                t += tstep;
+                if (t >= nco_len) t -= nco_len;
+            } else {
+                a = cscale(a, unit);
+                b = cscale(b, unit);
+            }
+            if (pr < npairs) *reinterpret_cast<float4 *>(xs + 2 * pr) = make_float4(a.x, a.y, b.x, b.y);
+        }
+    }
+}
+
+// the pre-scaled (cos, sin) table stage_span_pairs reads: nco_len + 1 entries
+template <int KIND>
+__device__ __forceinline__ void fill_nco_pairs(const StreamSrc &src, float2 *s_nco) {
+    const float unit = KIND == FMT_S16LE ? (1.0f / 32768.0f) : ((KIND == FMT_S8 || KIND == FMT_U8) ? 0.0078125f : 1.0f);
+    for (int i = threadIdx.x; i <= src.nco_len; i += blockDim.x) {
+        const int k = i == src.nco_len ? 0 : i;
+        s_nco[i] = make_float2(__ldg(src.nco_cos + k) * unit, __ldg(src.nco_sin + k) * unit);
+    }
+}
+
 template <int KIND, bool BANK_SMEM, int G>
 __global__ void __launch_bounds__(256) resample_fast_kernel(const ResampleFastArgs fa) {
     const ResampleArgs &a = fa.a;
@@ -303,6 +388,7 @@ struct ResampleTiledArgs {
     int B;           // blocks of M same-phase outputs per phase and CTA
     int A;           // ceil(nt / D) <= AMAX
     int AP;          // A rounded up to a multiple of 4
+    int nco_pairs;   // room for the pre-scaled (cos, sin) table behind the bank (0: none, stage_span does everything)
 };
 
 template <int KIND, int M, int AMAX>
@@ -331,7 +417,24 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiled
             hT[pb * AP + aa] = (aa < ta.A && t < a.nt) ? __ldg(a.bank + (size_t)p * a.nt + t) : 0.0f;
         }
     }
-    stage_span<KIND>(a.src, k_al, span, xs);
+    constexpr bool INTFMT = KIND == FMT_S8 || KIND == FMT_U8 || KIND == FMT_S16LE;
+    const bool mixing = a.src.nco_cos != nullptr;
+    if (INTFMT && k_al >= 0 && ((size_t)a.src.raw & 7) == 0 && (!mixing || ta.nco_pairs > a.src.nco_len)) {
+        float2 *s_nco = reinterpret_cast<float2 *>(hT + (size_t)a.I * a.D * AP);
+        if (mixing) {
+            fill_nco_pairs<KIND>(a.src, s_nco);
+            __syncthreads();
+        }
+        const int t0 = (int)(((long long)a.src.nco_idx + k_al) % (a.src.nco_len > 0 ? a.src.nco_len : 1));
+        stage_span_pairs<KIND>(a.src, k_al, span, xs, s_nco, t0);
+        if ((span & 1) && threadIdx.x == 0) {
+            float r, q;
+            fetch<KIND>(a.src, k_al + span - 1, r, q);
+            xs[span - 1] = make_float2(r, q);
+        }
+    } else {
+        stage_span<KIND>(a.src, k_al, span, xs);
+    }
     __syncthreads();
     for (int task = threadIdx.x; task < a.I * ta.B; task += blockDim.x) {
         const int r = task / ta.B, qb = task - r * ta.B;
@@ -372,62 +475,6 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiled
     }
 }
 
-
-// Staging for the hot case of the stripe kernel: integer IQ, the whole span inside this call's input (k_al >= 0), NCO
-// table in shared memory as (cos, sin) pairs.  A thread takes two consecutive samples per round -- one 64-bit (int16)
-// or 32-bit (8-bit IQ) load, magic-number conversion without I2F (rfa_fft_core.cuh decode_point), three packed FP32
-// instructions for the mixer (products rounded separately like the reference's tables, then -/+), one 128-bit
-// conflict-free store -- about a dozen instructions per sample where stage_span spends sixty.
-// `raw_s` != nullptr: the raw codes of the span already sit in shared memory (bulk copy), nothing waits on DRAM here.
-template <int KIND>
-__device__ __forceinline__ void stage_span_pairs(const StreamSrc &src, long long k_al, int span, float2 *xs, const float2 *s_nco,
-                                                 int t_first /* NCO index of sample k_al */, const void *raw_s = nullptr) {
-    const int nco_len = src.nco_len > 0 ? src.nco_len : 1;
-    const int npairs = span >> 1;  // an odd last sample is left to the caller
-    int t = (t_first + 2 * (int)threadIdx.x) % nco_len;
-    const int tstep = (2 * (int)blockDim.x) % nco_len;
-    const bool mixing = src.nco_cos != nullptr;
-    constexpr float unit = KIND == FMT_S16LE ? (1.0f / 32768.0f) : 0.0078125f;
-    constexpr int U = 8;  // loads in flight per thread: a chain of DRAM round trips otherwise
-    for (int pr0 = threadIdx.x; pr0 < npairs; pr0 += U * blockDim.x) {
-        uint32_t r0[U], r1[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int pr = pr0 + u * (int)blockDim.x;
-            r0[u] = r1[u] = 0u;
-            if (pr < npairs) {
-                if (KIND == FMT_S16LE) {
-                    const uint2 v = raw_s ? reinterpret_cast<const uint2 *>(raw_s)[pr]
-                                          : __ldg(reinterpret_cast<const uint2 *>((const uint32_t *)src.raw + k_al) + pr);
-                    r0[u] = v.x;
-                    r1[u] = v.y;
-                } else {
-                    const uint32_t v = raw_s ? reinterpret_cast<const uint32_t *>(raw_s)[pr]
-                                             : __ldg(reinterpret_cast<const uint32_t *>((const uint16_t *)src.raw + k_al) + pr);
-                    r0[u] = v & 0xFFFFu;
-                    r1[u] = v >> 16;
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int pr = pr0 + u * (int)blockDim.x;
-            cf a = decode_point<KIND>(r0[u], unit), b = decode_point<KIND>(r1[u], unit);
-            if (mixing) {
-                const int t1 = t + 1 == nco_len ? 0 : t + 1;
-                const float2 c0 = s_nco[t], c1 = s_nco[t1];
-                // re = r*c - q*s, im = q*c + r*s, every product rounded on its own (Signed8BitIQConverter.java:119-120)
-                const cf p0 = cscale(a, c0.x), q0 = cscale(cf{a.y, a.x}, c0.y);
-                a = cadd(p0, cf{-q0.x, q0.y});
-                const cf p1 = cscale(b, c1.x), q1 = cscale(cf{b.y, b.x}, c1.y);
-                b = cadd(p1, cf{-q1.x, q1.y});
-                t += tstep;
-                if (t >= nco_len) t -= nco_len;
-            }
-            if (pr < npairs) *reinterpret_cast<float4 *>(xs + 2 * pr) = make_float4(a.x, a.y, b.x, b.y);
-        }
-    }
-}
 
 // ---- K4 (+K2), stripe path for large decimation (RFA_SUM_FMA) -----------------------------------------------------
 // Airspy 10 Msps -> 96 kHz is I/D = 6/625 with 501 taps per phase: every input sample is used by 4.8 outputs, yet a
@@ -517,7 +564,7 @@ __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStri
                 if (i0 + u * (int)blockDim.x < nb) sbank[i0 + u * blockDim.x] = v[u];
         }
         if (a.src.nco_cos)
-            for (int i = threadIdx.x; i < a.src.nco_len; i += blockDim.x) s_nco[i] = make_float2(__ldg(a.src.nco_cos + i), __ldg(a.src.nco_sin + i));
+            fill_nco_pairs<KIND>(a.src, s_nco);
         if (threadIdx.x < 2) smem_stripe[sa.acc_pairs + threadIdx.x] = make_float2(0.0f, 0.0f);
     }
     const long long ntiles = (a.nout + a.tile - 1) / a.tile;
@@ -577,7 +624,17 @@ __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStri
         long long kn;
         int spn, tsn;
         tile_geom(tile + gridDim.x, &kn, &spn, &tsn);
-        if (tsn) tma_load_1d(s_raw, (const char *)a.src.raw + kn * BPS, (uint32_t)(tsn * BPS), &s_mbar);
+        if (tsn) {
+            tma_load_1d(s_raw, (const char *)a.src.raw + kn * BPS, (uint32_t)(tsn * BPS), &s_mbar);
+        } else if (INTFMT && kn >= 0) {
+            // no shared-memory room for the raw codes (two CTAs per SM): at least pull the next tile's span into L2
+            // while this tile's dot products run, so that its staging loads wait a third as long (whole 16-byte units
+            // inside the input only)
+            const size_t lo = ((size_t)a.src.raw + (size_t)kn * BPS + 15) & ~(size_t)15;
+            const size_t hi = ((size_t)a.src.raw + (size_t)(kn + spn) * BPS) & ~(size_t)15;
+            if (hi > lo)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+        }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int groups = (a.I + PH - 1) / PH, blocks = sa.TPC / TP;
@@ -812,7 +869,7 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
             const int warps = variant_b ? 12 : 8;
             sa.acc_pairs = (int)((tpc * I + 1) & ~1LL);
             sa.raw_bytes = (variant_b && in.kind <= 2) ? (int)(((size_t)sa.a.span_max * (in.kind == 2 ? 4 : 2) + 15) & ~(size_t)15) : 0;
-            sa.nco_pairs = in.nco_cos ? ((in.nco_len + 7) & ~7) : 8;
+            sa.nco_pairs = in.nco_cos ? ((in.nco_len + 1 + 7) & ~7) : 8;  // one entry more than the table: its entry 0 again
             const size_t ssmem = ((size_t)sa.a.span_max + 10 + sa.nco_pairs + sa.acc_pairs) * sizeof(float2) + (size_t)I * (nt + 2 * sa.pad) * sizeof(float) +
                                  (size_t)(2 * I + 2) * sizeof(int) + 16 + sa.raw_bytes;
             if (ssmem <= (variant_b ? 200 : 113) * 1024) {
@@ -852,7 +909,7 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
     }
     if (!exact && aligned && A >= 2 && A <= 12 && (size_t)I * D * 12 <= 8192) {
         // register-tiled path: M = 9 outputs per thread, B blocks per phase
-        constexpr int M = 9, kSpanT = 4096;  // 4 K samples per CTA: six CTAs per SM overlap staging and dot products
+        constexpr int M = 9, kSpanT = 3584;  // 3.5 K samples (+ bank + NCO table < 38 KB) per CTA: six CTAs per SM overlap staging and dot products
         const int span_cap = rs_span > 0 && rs_span < kSpanT ? rs_span : kSpanT;  // tuning knob "rs_span"
         const int amax = A <= 3 ? 3 : (A <= 5 ? 5 : (A <= 9 ? 9 : 12));
         long long B = ((long long)span_cap - 8 - (long long)(amax + 1) * D) / ((long long)M * D);  // span <= (B*M + amax + 1)*D + 4
@@ -870,11 +927,13 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
             if (threads > 256) threads = 256;
             const int span_used = (int)((B * M + amax + 1) * D + 8);
             ta.a.span_max = span_used;
-            const size_t tsmem = ((size_t)span_used + 8) * sizeof(float2) + (size_t)I * D * ta.AP * sizeof(float);
+            ta.nco_pairs = (in.nco_cos && in.kind <= 2) ? ((in.nco_len + 1 + 7) & ~7) : 0;
+            const size_t tsmem = ((size_t)span_used + 8) * sizeof(float2) + (size_t)I * D * ta.AP * sizeof(float) +
+                                 (size_t)ta.nco_pairs * sizeof(float2);
             static DeviceOnce tonce;
             int tdev = 0;
             const bool tfirst = tonce.pending(&tdev);
-            const int mx = (int)(((size_t)kSpanT + 8) * sizeof(float2) + 8192 * sizeof(float));
+            const int mx = (int)(((size_t)kSpanT + 8) * sizeof(float2) + 8192 * sizeof(float) + 512 * sizeof(float2));
 #define RFA_RT(KIND, AM)                                                                                           \
     do {                                                                                                           \
         if (tfirst)                                                                                                 \

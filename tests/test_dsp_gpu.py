@@ -370,3 +370,29 @@ def test_time_sharded_chain_matches_the_sequential_run(gpu_ctx, oracle, fmt, fs,
         fin = np.isfinite(want)
         assert np.array_equal(fin, np.isfinite(got_all)) and fin.sum() > 0.9 * len(want)
         assert np.abs(got_all[fin] - want[fin]).max() <= 1e-4 * np.abs(want[fin]).max()
+
+
+@pytest.mark.parametrize("fmt,fs,mode,width,packet", [(1, 2_400_000, 3, 100_000, 8192), (0, 20_000_000, 3, 100_000, 16384),
+                                                      (2, 10_000_000, 2, 10_000, 65536)])
+def test_fast_staging_is_bit_identical_to_the_general_staging(gpu_ctx, oracle, fmt, fs, mode, width, packet):
+    """The tiled and stripe resamplers stage 8-byte aligned integer IQ with a pair-per-thread path (magic-number
+    conversion, pre-scaled NCO table, fir.cu stage_span_pairs) and everything else -- history, unaligned buffers --
+    with the general one.  Both must produce the same BITS for a sample (else the audio of a stream would depend on
+    how it is cut into calls and tiles): the same stream from an aligned and from a 2- / 4-byte shifted device buffer.
+    (This is the test that caught ptxas contracting mul.rn.f32x2 + add.rn.f32x2 into FFMA2.)"""
+    import torch
+    import rfanalyzer_b200 as rfa
+    n = packet * 9
+    bps = rfa.BYTES_PER_SAMPLE[fmt]
+    iq = oracle.synth_iq(fmt, n).view(np.uint8)
+    outs = []
+    with torch.cuda.stream(gpu_ctx.torch_stream):
+        for off in (0, bps):
+            buf = torch.zeros(len(iq) + 16, dtype=torch.uint8, device="cuda")
+            buf[off:off + len(iq)] = torch.from_numpy(iq).cuda()
+            plan = rfa.ChainPlan(gpu_ctx, fmt, fs, 100_000_000, 100_000_000 + fs // 10, mode, width, packet, 1.0, rfa.SUM_FMA)
+            audio = torch.zeros(plan.max_audio(n), dtype=torch.float32, device="cuda")
+            got = plan.process(buf[off:off + len(iq)], n, audio)
+            gpu_ctx.sync()
+            outs.append(audio[:got].cpu().numpy())
+    assert len(outs[0]) > 100 and np.array_equal(outs[0], outs[1])
