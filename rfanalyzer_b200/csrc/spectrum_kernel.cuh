@@ -273,6 +273,20 @@ struct SpectrumFrame {
                     if (STORE) o[S * cc * P] = u[b * R + Dft<R>::perm(cc)];
             } else {
                 float *o = out + (c + S * (tid + b * T));
+#ifdef RFA_DB2
+                if (R % 2 == 0) {
+#pragma unroll
+                    for (int cc = 0; cc < R; cc += 2) {
+                        float d0, d1;
+                        logmag_db2(u[b * R + Dft<R>::perm(cc)], u[b * R + Dft<R>::perm(cc + 1)], inv_n2, d0, d1);
+                        if (STORE) o[shifted_offset(S * cc * P)] = d0;
+                        if (STORE) o[shifted_offset(S * (cc + 1) * P)] = d1;
+                        if (PEAK) pk[b * R + cc] = fmaxf(pk[b * R + cc], d0);
+                        if (PEAK) pk[b * R + cc + 1] = fmaxf(pk[b * R + cc + 1], d1);
+                    }
+                    continue;
+                }
+#endif
 #pragma unroll
                 for (int cc = 0; cc < R; cc++) {
 #ifdef RFA_EXP_NOEMIT
