@@ -1067,6 +1067,19 @@ cudaError_t fir_launch(const StreamDesc &in, const float *taps_re, const float *
     long long tile = (kSpanMax - ntaps) / dec;
     if (tile < 1) return cudaErrorInvalidValue;
     if (tile > 1024) tile = 1024;
+    // a short stream (the quadrature-rate filters behind a large decimation: 10^5 outputs per call) in 1024-output
+    // tiles is 79 CTAs on 148 SMs -- four CTAs per SM at least, down to one output per thread
+    {
+        static thread_local int sm_dev = -1, sms = 148;
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev != sm_dev) {
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+            sm_dev = dev;
+        }
+        long long fill = (nout + 4LL * sms - 1) / (4LL * sms);
+        fill = (fill + 255) / 256 * 256;
+        if (fill < tile) tile = fill;
+    }
     a.tile = (int)tile;
     a.real_only = real_only ? 1 : 0;
     a.out_re = out_re;
