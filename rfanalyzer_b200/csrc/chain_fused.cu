@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "pdl.h"
 
 namespace rfa {
 namespace {
@@ -31,6 +32,7 @@ constexpr int UT = 32;         // user filter taps at most (27 in the reference)
 
 template <bool EXACT, int TILE>
 __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
+    pdl_enter();
     // quadrature samples (user filter input) as (re, im) pairs; eight entries of slack in front: the last tap chunk of a
     // thread's first outputs looks (never uses) a few entries before the first staged sample
     __shared__ float2 s_q[8 + TILE + HALO + UT + 16];
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
 // Slides the delay lines of the user filter and of both decimators in one launch (FirFilter keeps the newest
 // taps-1 inputs): new = last `hist` samples of (old history ++ this call's `n` inputs).
 __global__ void chain_state_kernel(const ChainStateArgs a) {
+    pdl_enter();
     const int which = blockIdx.x;  // 0: user filter (complex), 1: first decimator, 2: second decimator
     const ChainStateArgs::Line &l = a.line[which];
     for (int h = threadIdx.x; h < l.hist; h += blockDim.x) {
@@ -213,21 +216,21 @@ cudaError_t fm_tail_launch(const FmTailArgs &a, bool exact, cudaStream_t st) {
     if (a.nu >= 2048LL * 512) {
         const unsigned grid = (unsigned)((a.nu + 2047) / 2048);
         if (exact)
-            fm_tail_kernel<true, 2048><<<grid, 256, 0, st>>>(a);
+            pdl_launch(fm_tail_kernel<true, 2048>, grid, 256, 0, st, a);
         else
-            fm_tail_kernel<false, 2048><<<grid, 256, 0, st>>>(a);
+            pdl_launch(fm_tail_kernel<false, 2048>, grid, 256, 0, st, a);
     } else {
         const unsigned grid = (unsigned)((a.nu + 511) / 512);
         if (exact)
-            fm_tail_kernel<true, 512><<<grid, 256, 0, st>>>(a);
+            pdl_launch(fm_tail_kernel<true, 512>, grid, 256, 0, st, a);
         else
-            fm_tail_kernel<false, 512><<<grid, 256, 0, st>>>(a);
+            pdl_launch(fm_tail_kernel<false, 512>, grid, 256, 0, st, a);
     }
     return cudaGetLastError();
 }
 
 cudaError_t chain_state_launch(const ChainStateArgs &a, cudaStream_t st) {
-    chain_state_kernel<<<3, 64, 0, st>>>(a);
+    pdl_launch(chain_state_kernel, 3, 64, 0, st, a);
     return cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "pdl.h"
 
 namespace rfa {
 namespace {
@@ -21,6 +22,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(256) fm_kernel(const float *__restrict__ re, const float *__restrict__ im,
                                                  long long n, const float *__restrict__ carry, float gain,
                                                  float volume, float *__restrict__ out) {
+    pdl_enter();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float r = re[i], q = im[i];
@@ -40,6 +42,7 @@ __global__ void __launch_bounds__(256) fm_kernel(const float *__restrict__ re, c
 }
 
 __global__ void carry_kernel(const float *re, const float *im, long long n, float *carry) {
+    pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0 && n > 0) {
         carry[0] = re[n - 1];
         carry[1] = im[n - 1];
@@ -49,6 +52,7 @@ __global__ void carry_kernel(const float *re, const float *im, long long n, floa
 // Demodulator.kt:293-297: power = re*re + im*im (each product rounded)
 __global__ void __launch_bounds__(256) power_kernel(const float *__restrict__ re, const float *__restrict__ im,
                                                     long long n, float *__restrict__ out) {
+    pdl_enter();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = __fadd_rn(__fmul_rn(re[i], re[i]), __fmul_rn(im[i], im[i]));
@@ -60,6 +64,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(256) packet_stats_kernel(const float *__restrict__ x, const long long *__restrict__ off,
                                                            int npackets, float *__restrict__ sum,
                                                            float *__restrict__ mx) {
+    pdl_enter();
     if (EXACT) {
         const int p = blockIdx.x * blockDim.x + threadIdx.x;
         if (p >= npackets) return;
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(256) packet_stats_kernel(const float *__restri
 // recurrence on them (the only sequential part, a few cycles per packet), everybody divides.
 __global__ void __launch_bounds__(256) agc_scan_kernel(const long long *off, int npackets, const float *sum,
                                                        const float *mx, float *state, float *gain, float *mean) {
+    pdl_enter();
     __shared__ float s_last[1024];
     __shared__ float s_carry;
     if (threadIdx.x == 0) s_carry = state[0];
@@ -135,6 +141,7 @@ template <bool SUBTRACT_MEAN>
 __global__ void __launch_bounds__(256) normalise_kernel(float *__restrict__ x, const long long *__restrict__ off,
                                                         const float *__restrict__ gain, const float *__restrict__ mean,
                                                         float volume, int npackets) {
+    pdl_enter();
     // gridDim.y is capped at 65535 by CUDA: a block row strides over the packets
     for (int p = blockIdx.y; p < npackets; p += gridDim.y) {
         const float g = gain[p], m = SUBTRACT_MEAN ? mean[p] : 0.0f;
@@ -159,17 +166,17 @@ cudaError_t demod_fm_launch(const float *re, const float *im, long long n, float
                             float *out, bool exact, int num_sms, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     if (exact)
-        fm_kernel<true><<<blocks_for(n, num_sms), 256, 0, st>>>(re, im, n, carry, gain, volume, out);
+        pdl_launch(fm_kernel<true>, blocks_for(n, num_sms), 256, 0, st, re, im, n, carry, gain, volume, out);
     else
-        fm_kernel<false><<<blocks_for(n, num_sms), 256, 0, st>>>(re, im, n, carry, gain, volume, out);
-    carry_kernel<<<1, 32, 0, st>>>(re, im, n, carry);  // Demodulator.kt:271-272
+        pdl_launch(fm_kernel<false>, blocks_for(n, num_sms), 256, 0, st, re, im, n, carry, gain, volume, out);
+    pdl_launch(carry_kernel, 1, 32, 0, st, re, im, n, carry);  // Demodulator.kt:271-272
     return cudaGetLastError();
 }
 
 cudaError_t demod_power_launch(const float *re, const float *im, long long n, float *out, int num_sms,
                                cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    power_kernel<<<blocks_for(n, num_sms), 256, 0, st>>>(re, im, n, out);
+    pdl_launch(power_kernel, blocks_for(n, num_sms), 256, 0, st, re, im, n, out);
     return cudaGetLastError();
 }
 
@@ -180,18 +187,18 @@ cudaError_t agc_launch(float *x, const long long *off, int npackets, long long m
     float *sum = scratch, *mx = scratch + npackets, *gain = scratch + 2 * (size_t)npackets,
           *mean = scratch + 3 * (size_t)npackets;
     if (exact)
-        packet_stats_kernel<true><<<(npackets + 63) / 64, 64, 0, st>>>(x, off, npackets, sum, mx);
+        pdl_launch(packet_stats_kernel<true>, (npackets + 63) / 64, 64, 0, st, x, off, npackets, sum, mx);
     else
-        packet_stats_kernel<false><<<npackets, 256, 0, st>>>(x, off, npackets, sum, mx);
-    agc_scan_kernel<<<1, 256, 0, st>>>(off, npackets, sum, mx, state, gain, mean);
+        pdl_launch(packet_stats_kernel<false>, npackets, 256, 0, st, x, off, npackets, sum, mx);
+    pdl_launch(agc_scan_kernel, 1, 256, 0, st, off, npackets, sum, mx, state, gain, mean);
     unsigned bx = (unsigned)((max_packet + 255) / 256);
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
     dim3 grid(bx, (unsigned)(npackets < 65535 ? npackets : 65535));
     if (subtract_mean)
-        normalise_kernel<true><<<grid, 256, 0, st>>>(x, off, gain, mean, volume, npackets);
+        pdl_launch(normalise_kernel<true>, grid, 256, 0, st, x, off, gain, mean, volume, npackets);
     else
-        normalise_kernel<false><<<grid, 256, 0, st>>>(x, off, gain, mean, volume, npackets);
+        pdl_launch(normalise_kernel<false>, grid, 256, 0, st, x, off, gain, mean, volume, npackets);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,7 @@
 
 #include "device_once.h"
 #include "kernels.h"
+#include "pdl.h"
 #include "rfa_fft_core.cuh"
 #include "spectrum_kernel.cuh"  // decode_point: magic-number sample conversion
 
@@ -96,6 +97,7 @@ struct ResampleArgs {
 
 template <int KIND, bool EXACT>
 __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
+    pdl_trigger();  // the small kernels behind the resampler may be scheduled now (pdl.h); they wait for this grid to finish
     extern __shared__ float smem[];
     float *sre = smem, *sim = smem + a.span_max;
     const long long j0 = (long long)blockIdx.x * a.tile;
@@ -313,6 +315,7 @@ __device__ __forceinline__ void fill_nco_pairs(const StreamSrc &src, float2 *s_n
 
 template <int KIND, bool BANK_SMEM, int G>
 __global__ void __launch_bounds__(256) resample_fast_kernel(const ResampleFastArgs fa) {
+    pdl_trigger();  // the small kernels behind the resampler may be scheduled now (pdl.h); they wait for this grid to finish
     const ResampleArgs &a = fa.a;
     extern __shared__ float2 xs[];  // [span_max + 8] samples, then the bank
     float *sbank = reinterpret_cast<float *>(xs + a.span_max + 8);
@@ -393,6 +396,7 @@ struct ResampleTiledArgs {
 
 template <int KIND, int M, int AMAX>
 __global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiledArgs ta) {
+    pdl_trigger();  // the small kernels behind the resampler may be scheduled now (pdl.h); they wait for this grid to finish
     const ResampleArgs &a = ta.a;
     constexpr int AP = (AMAX + 3) & ~3;
     extern __shared__ float2 xs[];  // [span_max + 8] samples, then the transposed bank [I][D][AP]
@@ -505,6 +509,7 @@ __device__ unsigned long long g_stripe_trace[8];
 #endif
 template <int KIND, int PH, int TP, bool DODD>
 __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStripeArgs sa) {
+    pdl_trigger();  // the small kernels behind the resampler may be scheduled now (pdl.h); they wait for this grid to finish
 #ifdef RFA_STRIPE_TRACE
     long long t_prev_ = clock64();
 #endif
@@ -744,6 +749,7 @@ struct FirArgs {
 
 template <bool CPLX, bool EXACT>
 __global__ void __launch_bounds__(256) fir_kernel(const FirArgs a) {
+    pdl_enter();
     extern __shared__ float smem[];
     float *sre = smem, *sim = smem + a.span_max;
     float *str_ = smem + 2 * a.span_max, *sti = str_ + a.ntaps;
@@ -796,6 +802,7 @@ __global__ void __launch_bounds__(256) fir_kernel(const FirArgs a) {
 // new history = the last `hist` samples of (old history ++ consumed input)
 template <int KIND>
 __global__ void history_kernel(const StreamSrc src, long long consumed, float *new_re, float *new_im) {
+    pdl_enter();
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= src.hist) return;
     float r, q;
@@ -1098,14 +1105,14 @@ cudaError_t fir_launch(const StreamDesc &in, const float *taps_re, const float *
     }
     if (taps_im) {
         if (exact)
-            fir_kernel<true, true><<<grid, 256, smem, st>>>(a);
+            pdl_launch(fir_kernel<true, true>, grid, 256, smem, st, a);
         else
-            fir_kernel<true, false><<<grid, 256, smem, st>>>(a);
+            pdl_launch(fir_kernel<true, false>, grid, 256, smem, st, a);
     } else {
         if (exact)
-            fir_kernel<false, true><<<grid, 256, smem, st>>>(a);
+            pdl_launch(fir_kernel<false, true>, grid, 256, smem, st, a);
         else
-            fir_kernel<false, false><<<grid, 256, smem, st>>>(a);
+            pdl_launch(fir_kernel<false, false>, grid, 256, smem, st, a);
     }
     return cudaGetLastError();
 }
@@ -1116,10 +1123,10 @@ cudaError_t history_launch(const StreamDesc &in, long long consumed, float *new_
     const StreamSrc s = make_src(in);
     const unsigned grid = (unsigned)((in.hist + 127) / 128);
     switch (in.kind) {
-        case 0: history_kernel<0><<<grid, 128, 0, st>>>(s, consumed, new_re, new_im); break;
-        case 1: history_kernel<1><<<grid, 128, 0, st>>>(s, consumed, new_re, new_im); break;
-        case 2: history_kernel<2><<<grid, 128, 0, st>>>(s, consumed, new_re, new_im); break;
-        case 3: history_kernel<3><<<grid, 128, 0, st>>>(s, consumed, new_re, new_im); break;
+        case 0: pdl_launch(history_kernel<0>, grid, 128, 0, st, s, consumed, new_re, new_im); break;
+        case 1: pdl_launch(history_kernel<1>, grid, 128, 0, st, s, consumed, new_re, new_im); break;
+        case 2: pdl_launch(history_kernel<2>, grid, 128, 0, st, s, consumed, new_re, new_im); break;
+        case 3: pdl_launch(history_kernel<3>, grid, 128, 0, st, s, consumed, new_re, new_im); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
