@@ -411,6 +411,34 @@ RFA_HD void pass_gather(const V *x, const cf *tw, int tid, V *u) {
     }
 }
 
+// Radix-32 pass with one butterfly per thread whose 31 twiddles W^(k r) are COMPOSED from ten table entries (r = 1, 2, 3
+// and r = 4, 8, ... 28) and 21 products: the last pass of the 16 x 32 x 32 plan (N = 16384) has a 127 KB table that
+// lives in L2, and 31 eight-byte loads per thread and frame with no registers to prefetch them were 27 % of that
+// kernel's stall cycles (ncu long_scoreboard, profiles/r01e_large_n_ncu_summary.txt).  One more rounding per twiddle.
+template <int NL, int T, int P, class V>
+RFA_HD void pass_gather_r32_composed(const V *x, const cf *tw, int tid, V *u) {
+    constexpr int R = 32, STR = NL / R;
+    static_assert(NL / T == R && STR % 16 == 0, "one radix-32 butterfly per thread");
+    const int k = tid & (P - 1);
+    const cf *twk = tw + k;
+    cf lo[4], hi[8];
+#pragma unroll
+    for (int r = 1; r < 4; r++) lo[r] = twk[(r - 1) * P];
+#pragma unroll
+    for (int j = 1; j < 8; j++) hi[j] = twk[(4 * j - 1) * P];
+    const V *xi = x + phys(tid);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        V v = xi[r * (STR + STR / 16)];
+        if (r > 0) {
+            const cf w = (r & 3) == 0 ? hi[r >> 2] : ((r >> 2) == 0 ? lo[r & 3] : cmul(lo[r & 3], hi[r >> 2]));
+            v = cmul(v, w);
+        }
+        u[r] = v;
+    }
+    Dft<R>::run(u);
+}
+
 // One pass, scatter side: natural-order output c of butterfly i goes to
 // y[(i-k)*R + k + c*P].  For P a multiple of 16 the c-offsets are immediates; the first
 // pass (P = 1, R = 16) writes 16 consecutive points, phys(16*i + c) = 17*i + c.

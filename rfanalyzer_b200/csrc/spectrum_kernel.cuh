@@ -203,7 +203,14 @@ struct SpectrumFrame {
     // `tw` is the base of the per-pass tables (global or the shared-memory copy)
     template <int PASS>
     static RFA_HD void gather(const cf *x, const cf *tw, int tid, cf *u) {
-        pass_gather<NL, T, PL::radix(PASS), PL::prod(PASS)>(x, tw + pass_tw_offset<NL>(PASS), tid, u);
+#ifndef RFA_NO_TWCOMPOSE
+        // both radix-32 passes of the 16 x 32 x 32 plan (N = 16384): 64.8 -> 60.1 us (int8), 74.1 -> 69.6 us (int16) per 2^24
+        // samples, profiles/r02h_16384_composed_twiddles.txt
+        if constexpr (PASS > 0 && PL::radix(PASS) == 32 && E == 32 && !(PASS == LAST && LAST_TW_REG))
+            pass_gather_r32_composed<NL, T, PL::prod(PASS)>(x, tw + pass_tw_offset<NL>(PASS), tid, u);
+        else
+#endif
+            pass_gather<NL, T, PL::radix(PASS), PL::prod(PASS)>(x, tw + pass_tw_offset<NL>(PASS), tid, u);
     }
     // last pass with its twiddles held by the thread: twreg[b*(R-1) + r-1]
     static RFA_HD void load_last_tw(const cf *tw, int tid, cf *twreg) {
