@@ -290,8 +290,11 @@ def other_configs(torch, rfa, ctx, stream, peak_gbs, with_cpu):
         for j, b in enumerate(iqs):
             rfa.synth_iq(ctx, rfa.FMT_S8, S, b, first=j * S)
         rows = [torch.empty(S, dtype=torch.float32, device="cuda") for _ in range(nset)]
-        for n in (1024, 2048, 8192, 16384, 32768, 65536):
+        # (n, cluster): the last two entries time the thread-block-cluster path for N >= 32768 (knob "cluster" = 1: the
+        # four-step intermediate in distributed shared memory -- a sixth of the DRAM traffic, slower)
+        for n, cluster in ((1024, 0), (2048, 0), (8192, 0), (16384, 0), (32768, 0), (65536, 0), (32768, 1), (65536, 1)):
             frames = S // n
+            ctx.set_option("cluster", cluster)
             plan = rfa.SpectrumPlan(ctx, rfa.FMT_S8, n, avg_len=AVG_LEN, peak_hold=True)
             peaks = torch.zeros(n, dtype=torch.float32, device="cuda")
             avg = torch.zeros(n, dtype=torch.float32, device="cuda")
@@ -305,16 +308,18 @@ def other_configs(torch, rfa, ctx, stream, peak_gbs, with_cpu):
             l0 = ctx.launch_count
             ms = time_calls(torch, stream, call, 60)
             alg = plan.algorithmic_bytes(frames, True)
-            line = {"workload": "C3: int8 IQ @20 Msps, %d-pt FFT, rows + peak hold + avg=8, 2^24 samples per call" % n,
+            line = {"workload": "C3: int8 IQ @20 Msps, %d-pt FFT, rows + peak hold + avg=8, 2^24 samples per call%s" % (
+                        n, " (cluster path: intermediate in distributed shared memory)" if cluster else ""),
                     "Msamples_per_s": S / ms / 1e3, "us_per_call": ms * 1e3, "algorithmic_GBps": alg / ms / 1e6,
                     "frac_of_hbm_peak": alg / ms / 1e6 / peak_gbs, "launches_per_call": (ctx.launch_count - l0) / 60}
-            if O is not None and O.ref_available():
+            if O is not None and O.ref_available() and not cluster:
                 h = O.synth_iq(rfa.FMT_S8, 1 << 22)
                 cpu_reference_pass(h, cores, 1, n)
                 v, dt = cpu_reference_pass(h, cores, 4, n)
                 line["cpu_reference"] = {"Msamples_per_s": v, "cores": cores, "sample": "4 passes over 2^22 samples (%.2f s)" % dt}
-            out["C3_fft_%d" % n] = line
+            out["C3_fft_%d%s" % (n, "_cluster" if cluster else "")] = line
             plan.close()
+        ctx.set_option("cluster", 0)
         del rows, iqs
     # ---- C2 / C4: IQ -> audio chains, 2^24 samples per call, device-resident
     chains = [("C2_wfm", "C2: RTL-SDR uint8 @2.4 Msps -> mixer + resampler to 384 kHz -> wFM -> 48 kHz audio", rfa.FMT_U8, 2_400_000, rfa.MODE_WFM, 100_000, 8192),

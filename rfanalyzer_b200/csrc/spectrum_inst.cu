@@ -238,18 +238,17 @@ cudaError_t launch_size(const SpectrumLaunch &L, bool query, int *grid, int *spc
             switch (L.in_fmt) {
                 case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB, true>(L, query, grid, spc);
                 case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB, true>(L, query, grid, spc);
-                case FMT_S16LE:
-                    if constexpr (NL <= 4096)  // at 8192 two 32 KB chunk buffers no longer fit beside the frames and tables
-                        return launch_one<NL, S, FMT_S16LE, OUT_DB, true>(L, query, grid, spc);
-                    break;
+                // (at 8192 two 32 KB chunk buffers no longer fit beside the frames and tables: one buffer, stage_buffers())
+                case FMT_S16LE: return launch_one<NL, S, FMT_S16LE, OUT_DB, true>(L, query, grid, spc);
             }
         }
     }
-    if constexpr (S == 1 && NL == 16384) {  // 8-bit IQ: two 32 KB chunk buffers fit beside the 139 KB exchange frame
+    if constexpr (S == 1 && NL == 16384) {  // two 32 KB chunk buffers (8-bit IQ) or one of 64 KB (int16) beside the 139 KB exchange frame
         if (staged_enabled(L)) {
             switch (L.in_fmt) {
                 case FMT_S8: return launch_one<NL, S, FMT_S8, OUT_DB, true>(L, query, grid, spc);
                 case FMT_U8: return launch_one<NL, S, FMT_U8, OUT_DB, true>(L, query, grid, spc);
+                case FMT_S16LE: return launch_one<NL, S, FMT_S16LE, OUT_DB, true>(L, query, grid, spc);
             }
         }
     }

@@ -527,10 +527,16 @@ __device__ __forceinline__ void retire_cta(const SpectrumParams &p) {
     }
 }
 
-// bytes of shared memory a STAGED kernel needs on top of SpectrumFrame::SMEM_BYTES: two chunk buffers
+// chunk buffers of a STAGED kernel: a two-deep ring, or ONE buffer where two no longer fit beside the exchange frames
+// (int16 IQ at N >= 8192: the refill issued after the first exchange barrier then has the rest of the frame to land)
+template <int NL, int IN>
+RFA_CX int stage_buffers() {
+    return (IN == FMT_S16LE && NL >= 8192) ? 1 : 2;
+}
+// bytes of shared memory a STAGED kernel needs on top of SpectrumFrame::SMEM_BYTES
 template <int NL, int IN>
 RFA_CX size_t staged_bytes() {
-    return 2 * (size_t)Geom<NL>::FPC * NL * in_elem_bytes<IN>();
+    return (size_t)stage_buffers<NL, IN>() * Geom<NL>::FPC * NL * in_elem_bytes<IN>();
 }
 template <int NL, int S, int IN, int OUT>
 RFA_CX size_t staged_offset() {  // 128-byte aligned start of the chunk buffers
@@ -587,12 +593,13 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
     uint32_t raw[F::PREFETCH ? E : 1];
     constexpr size_t CHUNK_BYTES = (size_t)FPC * NL * BPS;
     unsigned char *stage = smem_raw + staged_offset<NL, S, IN, OUT>();  // [2][CHUNK_BYTES] (STAGED)
-    auto start_chunks = [&]() {  // thread 0: the first two chunks start moving
+    constexpr int NSTG = STAGED ? stage_buffers<NL, IN>() : 2;
+    auto start_chunks = [&]() {  // thread 0: the first chunks start moving
         mbar_init(&s_mbar[0]);
         mbar_init(&s_mbar[1]);
         const int qs[2] = {q, q_next};
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NSTG; b++) {
             long long f0;
             uint32_t bytes;
             chunk_block<NL, FPC, BPS>(p.nframes, qs[b], &f0, &bytes);
@@ -662,23 +669,26 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
         if constexpr (STAGED) {
             // this chunk's raw IQ sits in buffer it & 1 (copy issued two iterations ago); the buffer is
             // refilled with chunk q_next2 right after the first exchange barrier of this iteration
+            // (one buffer, NSTG == 1: copy issued one iteration ago, refilled with chunk q_next)
             long long f0;
             uint32_t bytes;
             chunk_block<NL, FPC, BPS>(p.nframes, q, &f0, &bytes);
-            mbar_wait(&s_mbar[it & 1], (uint32_t)((it >> 1) & 1));
+            const int sb = NSTG == 2 ? (it & 1) : 0;
+            mbar_wait(&s_mbar[sb], (uint32_t)((NSTG == 2 ? (it >> 1) : it) & 1));
             if (active) {
                 if constexpr (F::PREFETCH) {
-                    F::load_raw((const char *)(stage + (it & 1) * CHUNK_BYTES) + ((f - f0) * (long long)NL + tid) * BPS, raw);
+                    F::load_raw((const char *)(stage + sb * CHUNK_BYTES) + ((f - f0) * (long long)NL + tid) * BPS, raw);
                     F::first_from_raw(raw, wreg, u);
                 } else {  // 32 points per thread: convert straight out of the staged chunk
-                    F::first(p, f, c, tid, wreg, u, (const char *)(stage + (it & 1) * CHUNK_BYTES) + (f - f0) * (long long)NL * BPS);
+                    F::first(p, f, c, tid, wreg, u, (const char *)(stage + sb * CHUNK_BYTES) + (f - f0) * (long long)NL * BPS);
                 }
             }
-            if (q_next2 < nchunks) {
-                chunk_block<NL, FPC, BPS>(p.nframes, q_next2, &f0, &sn.bytes);
-                sn.dst = stage + (it & 1) * CHUNK_BYTES;
+            const int q_refill = NSTG == 2 ? q_next2 : q_next;
+            if (q_refill < nchunks) {
+                chunk_block<NL, FPC, BPS>(p.nframes, q_refill, &f0, &sn.bytes);
+                sn.dst = stage + sb * CHUNK_BYTES;
                 sn.src = (const char *)p.in + f0 * (long long)NL * BPS;
-                sn.mbar = &s_mbar[it & 1];
+                sn.mbar = &s_mbar[sb];
             }
         } else if constexpr (F::PREFETCH) {
             if (active) F::first_from_raw(raw, wreg, u);

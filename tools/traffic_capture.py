@@ -25,6 +25,8 @@ F = S // N
 NBUF = 8
 stream = torch.cuda.Stream()
 ctx = rfa.Context(0, stream)
+for kv in filter(None, os.environ.get("KNOBS", "").split(",")):  # e.g. KNOBS=cluster=1 with N=65536
+    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 plan = rfa.SpectrumPlan(ctx, FMT, N, avg_len=8)
 bps = rfa.BYTES_PER_SAMPLE[FMT]
 with torch.cuda.stream(stream):
