@@ -340,10 +340,17 @@ struct Dft<32> {
 // Radix plan of an n-point transform, shared by the kernels (Plan<NL>) and the host table builder
 // (make_pass_twiddles): as many radix-16 passes as fit, then one radix-2/4/8 pass -- except for
 // 16384 points, where a thread holds 32 points and 16 x 32 x 32 saves a whole pass (and exchange).
+#ifdef RFA_R8  // timing experiment: N = 4096 as 8 x 8 x 8 x 8 with 8 points per thread (512 threads per frame, <= 64 registers)
+RFA_CX int plan_passes(int lg) { return lg == 12 ? 4 : (lg == 14 ? 3 : lg / 4 + (lg % 4 ? 1 : 0)); }
+RFA_CX int plan_radix(int lg, int pass) {
+    return lg == 12 ? 8 : (lg == 14 ? (pass == 0 ? 16 : 32) : (pass < lg / 4 ? 16 : (1 << (lg % 4))));
+}
+#else
 RFA_CX int plan_passes(int lg) { return lg == 14 ? 3 : lg / 4 + (lg % 4 ? 1 : 0); }
 RFA_CX int plan_radix(int lg, int pass) {
     return lg == 14 ? (pass == 0 ? 16 : 32) : (pass < lg / 4 ? 16 : (1 << (lg % 4)));
 }
+#endif
 
 template <int NL>
 struct Plan {

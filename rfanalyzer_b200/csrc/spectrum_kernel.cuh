@@ -56,7 +56,11 @@ struct SpectrumParams {
 
 template <int NL>
 struct Geom {
+#ifdef RFA_R8
+    static constexpr int T = NL == 4096 ? 512 : (NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1)));
+#else
     static constexpr int T = NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1));
+#endif
     static constexpr int E = NL / T;
     static constexpr int FPC = T >= 256 ? 1 : 256 / T;   // frames per CTA
     static constexpr int CTA = T * FPC;
@@ -554,7 +558,11 @@ __device__ __forceinline__ void chunk_block(long long nframes, int q, long long 
 }
 
 template <int NL, int S, int IN, int OUT, bool STAGED = false>
+#ifdef RFA_R8
+__global__ void __launch_bounds__(Geom<NL>::CTA, (Geom<NL>::CTA <= 256 || NL == 4096) ? RFA_MINCTAS : 1) spectrum_kernel(const SpectrumParams p) {
+#else
 __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINCTAS : 1) spectrum_kernel(const SpectrumParams p) {
+#endif
     using G = Geom<NL>;
     using F = SpectrumFrame<NL, S, IN, OUT>;
     constexpr int T = G::T, E = G::E, FPC = G::FPC, N = NL * S;

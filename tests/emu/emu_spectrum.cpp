@@ -439,7 +439,9 @@ static int emu_dispatch(int N, int in_fmt, int out_kind, int window_kind, const 
             case 512: return emu_two_fmt<512>(in_fmt, p, peaks);
             case 1024: return emu_two_fmt<1024>(in_fmt, p, peaks);
             case 2048: return emu_two_fmt<2048>(in_fmt, p, peaks);
+#ifndef RFA_R8  // (the radix-8 experiment changes Plan<4096>, which the dual-frame kernel does not follow)
             case 4096: return emu_two_fmt<4096>(in_fmt, p, peaks);
+#endif
         }
         return -1;
     }
