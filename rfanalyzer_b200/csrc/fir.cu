@@ -533,16 +533,16 @@ __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStri
     if (tma_ok && threadIdx.x == 0) mbar_init(&s_mbar);
     unsigned int waits = 0;  // completed bulk copies so far (CTA-uniform): the mbarrier's phase parity
     // geometry of a tile: first staged sample, samples, and how many of them a bulk copy may fetch
-    auto tile_geom = [&](long long tile, long long *k_al_out, int *span_out, int *tma_samples) {
-        const long long j0t = tile * a.tile;
-        const long long T0t = (long long)a.ph0 + j0t * a.D;
-        const long long k_first = a.rel + T0t / a.I;
-        long long k_hi = a.rel + (T0t + (long long)(a.I - 1) * a.D) / a.I + (long long)(sa.TPC - 1) * a.D;
-        const long long k_end = a.rel + ((long long)a.ph0 + (a.nout - 1) * a.D) / a.I;  // newest sample any output needs
+    // A tile is addressed by (qT, rT) = (T0 / I, T0 % I) of its first output's polyphase time T0 = ph0 + j0 * D; the CTA
+    // steps from one of its tiles to the next by a constant (dq, dr), so the tile loop carries no 64-bit division.
+    const long long k_end = a.rel + ((long long)a.ph0 + (a.nout - 1) * a.D) / a.I;  // newest sample any output needs
+    auto tile_geom = [&](long long qT, int rT, long long *k_al_out, int *span_out, int *tma_samples) {
+        const long long k_first = a.rel + qT;
+        long long k_hi = k_first + (rT + (a.I - 1) * a.D) / a.I + (long long)(sa.TPC - 1) * a.D;
         if (k_hi > k_end) k_hi = k_end;  // last tile: never read past the input
         const long long k_lo = k_first - (a.nt - 1);
         constexpr int AL = 16 / BPS;  // a bulk copy starts on a 16-byte boundary of the input
-        const long long k_al = k_lo - (((k_lo % AL) + AL) % AL);
+        const long long k_al = k_lo & ~(long long)(AL - 1);
         const int span = (int)(k_hi - k_al + 1);
         *k_al_out = k_al;
         *span_out = span;
@@ -551,6 +551,16 @@ __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStri
         if ((long long)ts * BPS > sa.raw_bytes) ts = 0;
         *tma_samples = ts;
     };
+    long long qT;
+    int rT;
+    {
+        const long long T0first = (long long)a.ph0 + (long long)blockIdx.x * a.tile * a.D;
+        qT = T0first / a.I;
+        rT = (int)(T0first % a.I);
+    }
+    const long long dT = (long long)gridDim.x * a.tile * a.D;
+    const long long dq = dT / a.I;
+    const int dr = (int)(dT % a.I);
     // once per CTA: the polyphase bank (zero taps around every row, so that the inner loop needs no range test) and
     // the NCO table; every load is issued before the first one is consumed -- a load/store pair per iteration is a
     // chain of L2 round trips.  Then the CTA walks tiles blockIdx.x, +gridDim.x, ...
@@ -578,21 +588,27 @@ __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStri
     if (threadIdx.x == 0 && (long long)blockIdx.x < ntiles) {  // the first tile's raw codes start moving right away
         long long k0;
         int sp0, ts0;
-        tile_geom(blockIdx.x, &k0, &sp0, &ts0);
+        tile_geom(qT, rT, &k0, &sp0, &ts0);
         if (ts0) tma_load_1d(s_raw, (const char *)a.src.raw + k0 * BPS, (uint32_t)(ts0 * BPS), &s_mbar);
     }
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long j0 = tile * a.tile;
-    const long long T0 = (long long)a.ph0 + j0 * a.D;
     long long k_al;
     int span, tma_samples;
-    tile_geom(tile, &k_al, &span, &tma_samples);
+    tile_geom(qT, rT, &k_al, &span, &tma_samples);
+    // the CTA's next tile
+    long long qN = qT + dq;
+    int rN = rT + dr;
+    if (rN >= a.I) {
+        rN -= a.I;
+        qN++;
+    }
     __syncthreads();  // the previous tile's warps are done with xs, the slot table and the output accumulators
     for (int i = threadIdx.x; i < sa.acc_pairs; i += blockDim.x) smem_stripe[i] = make_float2(0.0f, 0.0f);
-    if ((int)threadIdx.x < a.I) {  // the 64-bit divisions happen once per tile, not once per warp task
-        const long long T = T0 + (long long)threadIdx.x * a.D;
-        s_slot[2 * threadIdx.x] = (int)(a.rel + T / a.I - k_al);
-        s_slot[2 * threadIdx.x + 1] = (int)(T % a.I) * RS + sa.pad;
+    if ((int)threadIdx.x < a.I) {  // phase slot s of the tile: T = T0 + s * D
+        const int e = rT + (int)threadIdx.x * a.D;  // < I + I * D: 32-bit
+        s_slot[2 * threadIdx.x] = (int)(a.rel + qT + e / a.I - k_al);
+        s_slot[2 * threadIdx.x + 1] = (e % a.I) * RS + sa.pad;
     }
     const bool fast = INTFMT && k_al >= 0 && ((size_t)a.src.raw & 7) == 0;
     if (fast) {
@@ -628,7 +644,7 @@ __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStri
     if (threadIdx.x == 0 && tile + gridDim.x < ntiles) {  // the raw buffer is free: fetch the next tile under the dot products
         long long kn;
         int spn, tsn;
-        tile_geom(tile + gridDim.x, &kn, &spn, &tsn);
+        tile_geom(qN, rN, &kn, &spn, &tsn);
         if (tsn) {
             tma_load_1d(s_raw, (const char *)a.src.raw + kn * BPS, (uint32_t)(tsn * BPS), &s_mbar);
         } else if (INTFMT && kn >= 0) {
@@ -732,6 +748,8 @@ __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStri
         }
     }
     STRIPE_STAMP(5);  // dot products (warp 0's tasks)
+    qT = qN;
+    rT = rN;
   }  // tiles
 }
 
