@@ -508,7 +508,20 @@ __device__ unsigned long long g_stripe_trace[8];
 #define STRIPE_STAMP(k) do {} while (0)
 #endif
 template <int KIND, int PH, int TP, bool DODD>
+__device__ __forceinline__ void resample_stripe_body(const ResampleStripeArgs &sa);
+template <int KIND, int PH, int TP, bool DODD>
 __global__ void __launch_bounds__(512) resample_stripe_kernel(const ResampleStripeArgs sa) {
+    resample_stripe_body<KIND, PH, TP, DODD>(sa);
+}
+// the same body for two CTAs of TWELVE warps per SM (<= 85 registers; the default): a tile of I = 6 phases is six warp
+// tasks, split in two over the sample range that is twelve -- no warp idles at the tile's barrier, which was the
+// eight-warp kernel's top stall (ncu: 1.7 cycles per issue).  nFM 221 -> 209 us per 2^26 samples.
+template <int KIND, int PH, int TP, bool DODD>
+__global__ void __launch_bounds__(384, 2) resample_stripe12_kernel(const ResampleStripeArgs sa) {
+    resample_stripe_body<KIND, PH, TP, DODD>(sa);
+}
+template <int KIND, int PH, int TP, bool DODD>
+__device__ __forceinline__ void resample_stripe_body(const ResampleStripeArgs &sa) {
     pdl_trigger();  // the small kernels behind the resampler may be scheduled now (pdl.h); they wait for this grid to finish
 #ifdef RFA_STRIPE_TRACE
     long long t_prev_ = clock64();
@@ -888,10 +901,11 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
             sa.a.span_max = (int)(tpc * D + nt + D + 24);
             const int groups = (I + PH - 1) / PH, tasks = groups * (int)(tpc / TP);
             (void)tasks;
-            // variant A (default): two persistent CTAs of eight warps per SM, raw IQ loaded by the threads;
+            // default: two persistent CTAs of twelve warps per SM, raw IQ loaded by the threads (knob rs_span = 1: eight warps);
             // variant B (knob rs_span = 2): one CTA of twelve warps per SM, the next tile's raw IQ arrives by bulk copy
             const bool variant_b = rs_span == 2;
-            const int warps = variant_b ? 12 : 8;
+            const bool variant_d = rs_span != 1 && rs_span != 2;  // the default; knob rs_span = 1: eight warps per CTA (97 registers)
+            const int warps = (variant_b || variant_d) ? 12 : 8;
             sa.acc_pairs = (int)((tpc * I + 1) & ~1LL);
             sa.raw_bytes = (variant_b && in.kind <= 2) ? (int)(((size_t)sa.a.span_max * (in.kind == 2 ? 4 : 2) + 15) & ~(size_t)15) : 0;
             sa.nco_pairs = in.nco_cos ? ((in.nco_len + 1 + 7) & ~7) : 8;  // one entry more than the table: its entry 0 again
@@ -915,8 +929,13 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
 #define RFA_STRIPE(KIND, DO)                                                                                                    \
     do {                                                                                                                        \
         if (sfirst) cudaFuncSetAttribute(resample_stripe_kernel<KIND, PH, TP, DO>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); \
-        if (launch_now && in.kind == KIND && dodd == DO)                                                                        \
-            resample_stripe_kernel<KIND, PH, TP, DO><<<sgrid, 32 * warps, ssmem, st>>>(sa);                                     \
+        if (sfirst) cudaFuncSetAttribute(resample_stripe12_kernel<KIND, PH, TP, DO>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); \
+        if (launch_now && in.kind == KIND && dodd == DO) {                                                                      \
+            if (variant_d)                                                                                                      \
+                resample_stripe12_kernel<KIND, PH, TP, DO><<<sgrid, 32 * warps, ssmem, st>>>(sa);                               \
+            else                                                                                                                \
+                resample_stripe_kernel<KIND, PH, TP, DO><<<sgrid, 32 * warps, ssmem, st>>>(sa);                                 \
+        }                                                                                                                       \
     } while (0)
                 if (in.kind < 0 || in.kind > 3) return cudaErrorInvalidValue;
                 for (int pass = sfirst ? 0 : 1; pass < 2; pass++) {
