@@ -953,7 +953,9 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
     }
     if (!exact && aligned && A >= 2 && A <= 12 && (size_t)I * D * 12 <= 8192) {
         // register-tiled path: M = 9 outputs per thread, B blocks per phase
-        constexpr int M = 9, kSpanT = 3584;  // 3.5 K samples (+ bank + NCO table < 38 KB) per CTA: six CTAs per SM overlap staging and dot products
+        // 4 K samples (+ bank + NCO table = 40 KB) per CTA: B = 16 blocks per phase, so that the 32 tasks of a warp share ONE
+        // phase and their tap loads are broadcasts; registers (64 x 256) allow four CTAs per SM, shared memory five
+        constexpr int M = 9, kSpanT = 4096;
         const int span_cap = rs_span > 0 && rs_span < kSpanT ? rs_span : kSpanT;  // tuning knob "rs_span"
         const int amax = A <= 3 ? 3 : (A <= 5 ? 5 : (A <= 9 ? 9 : 12));
         long long B = ((long long)span_cap - 8 - (long long)(amax + 1) * D) / ((long long)M * D);  // span <= (B*M + amax + 1)*D + 4
