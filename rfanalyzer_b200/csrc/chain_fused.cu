@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "rfa_fft_core.cuh"  // cf, caxpy (packed FFMA2)
 #include "pdl.h"
 
 namespace rfa {
@@ -115,9 +116,13 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
     constexpr int M = (TILE + HALO + 255) / 256;  // 9 (TILE 2048) / 3 (TILE 512): odd, so that lanes M samples apart hit distinct banks
     static_assert(M % 2 == 1, "M must be odd");
     for (int s0 = threadIdx.x * M; s0 < nus; s0 += blockDim.x * M) {
-        float ar[M], ai[M];
+        float ar[M], ai[M];  // (RFA_SUM_FMA keeps the pair in `ac` instead: one packed multiply-add per tap and output)
+        cf ac[M];
 #pragma unroll
-        for (int m = 0; m < M; m++) ar[m] = ai[m] = 0.0f;
+        for (int m = 0; m < M; m++) {
+            ar[m] = ai[m] = 0.0f;
+            ac[m] = cf{0.0f, 0.0f};
+        }
         for (int t0 = 0; t0 < a.user_taps; t0 += 8) {
             const float2 *xw = xq + (s0 + a.user_taps - 8 - t0);  // sample of (output s0, tap t0 + 7)
             float2 w[M + 7];
@@ -130,8 +135,12 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
                 if (t0 + j < a.user_taps) {  // CTA-uniform
 #pragma unroll
                     for (int m = 0; m < M; m++) {
-                        ar[m] = mac<EXACT>(ar[m], h[j], w[7 + m - j].x);
-                        ai[m] = mac<EXACT>(ai[m], h[j], w[7 + m - j].y);
+                        if constexpr (EXACT) {
+                            ar[m] = mac<EXACT>(ar[m], h[j], w[7 + m - j].x);
+                            ai[m] = mac<EXACT>(ai[m], h[j], w[7 + m - j].y);
+                        } else {
+                            ac[m] = caxpy(h[j], cf{w[7 + m - j].x, w[7 + m - j].y}, ac[m]);
+                        }
                     }
                 }
             }
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
         for (int m = 0; m < M; m++) {
             const int sm = s0 + m;
             if (sm < nus) {
-                float vr = ar[m], vi = ai[m];
+                float vr = EXACT ? ar[m] : ac[m].x, vi = EXACT ? ai[m] : ac[m].y;
                 if (ulo + sm == -1) {  // the sample before this call's first one: the discriminator's carry
                     vr = a.carry_in[0];
                     vi = a.carry_in[1];
@@ -188,23 +197,49 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
     if ((dlo + (a.a1_taps - 1) - a.first_a1) < 0) m_lo = -((-(dlo + (a.a1_taps - 1) - a.first_a1)) / 2);
     long long m_hi = (u1 - 1 - a.first_a1) >= 0 ? (u1 - 1 - a.first_a1) / 2 : -1;  // last m with newest tap <= u1-1
     const int nm = (int)(m_hi - m_lo + 1);
-    for (int s = threadIdx.x; s < nm; s += blockDim.x) {
-        const long long m = m_lo + s;
-        float v = 0.0f;
-        if (m >= 0) {
-            const long long newest = a.first_a1 + 2 * m;
-            const int pos = (int)(newest - dlo) + 1;
-            float acc = 0.0f;
-            for (int t = 0; t < a.a1_taps; t++) acc = mac<EXACT>(acc, s_t1[t], s_dem[pos - t]);
-            v = acc;
-            if (newest >= u0 && m < a.n1) {
-                if (a.a1_out) a.a1_out[m] = v;
-                if (a.ratio == 2) a.audio[m] = v;
-            }
-        } else if (m + a.a2_hist >= 0 && a.hist_a2) {
-            v = a.hist_a2[m + a.a2_hist];  // first-decimator outputs of earlier calls: the second decimator's delay line
+    // A thread owns MD = 5 consecutive outputs (their windows slide by two samples: 17 loads for 45 multiply-adds instead of
+    // two loads per multiply-add; an odd MD keeps the lanes' 10-float stride at a two-way bank conflict, like the stride of
+    // two it replaces), taps in registers, in the reference's order.
+    constexpr int MD = 5;
+    float h1[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) h1[t] = t < a.a1_taps ? s_t1[t] : 0.0f;
+    for (int s0 = threadIdx.x * MD; s0 < nm; s0 += blockDim.x * MD) {
+        const int pos0 = (int)(a.first_a1 + 2 * (m_lo + s0) - dlo) + 1;  // s_dem index of output s0's newest sample
+        float w[2 * MD + 7];
+#pragma unroll
+        for (int i = 0; i < 2 * MD + 7; i++) {
+            const int idx = pos0 - 8 + i;
+            w[i] = (idx >= 0 && idx < TILE + HALO) ? s_dem[idx] : 0.0f;
         }
-        s_a1[s] = v;
+        float acc[MD];
+#pragma unroll
+        for (int k = 0; k < MD; k++) acc[k] = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            if (t < a.a1_taps) {  // CTA-uniform
+#pragma unroll
+                for (int k = 0; k < MD; k++) acc[k] = mac<EXACT>(acc[k], h1[t], w[8 + 2 * k - t]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MD; k++) {
+            const int sk = s0 + k;
+            if (sk < nm) {
+                const long long m = m_lo + sk;
+                float v = 0.0f;
+                if (m >= 0) {
+                    v = acc[k];
+                    if (a.first_a1 + 2 * m >= u0 && m < a.n1) {
+                        if (a.a1_out) a.a1_out[m] = v;
+                        if (a.ratio == 2) a.audio[m] = v;
+                    }
+                } else if (m + a.a2_hist >= 0 && a.hist_a2) {
+                    v = a.hist_a2[m + a.a2_hist];  // first-decimator outputs of earlier calls: the second decimator's delay line
+                }
+                s_a1[sk] = v;
+            }
+        }
     }
     if (a.ratio != 8) return;
     __syncthreads();
