@@ -449,6 +449,7 @@ __global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiled
 #pragma unroll
         for (int m = 0; m < M; m++) acc[m] = cf{0.0f, 0.0f};
         const float *hp = hT + (size_t)phase * a.D * AP;
+#pragma unroll 5  // sample and tap addresses become immediates inside the unrolled body (15 of 121 instructions per b were address updates)
         for (int b = 0; b < a.D; b++) {
             float h[AP];
 #pragma unroll
