@@ -783,11 +783,19 @@ template <bool CPLX, bool EXACT>
 __global__ void __launch_bounds__(256) fir_kernel(const FirArgs a) {
     pdl_enter();
     extern __shared__ float smem[];
+    // RFA_SUM_EXACT: planar samples and taps, every product and sum rounded on its own, in the reference's order.
+    // RFA_SUM_FMA: samples and taps INTERLEAVED as (re, im) pairs in the same shared memory -- one 64-bit load each per
+    // tap and one (real taps) or two (complex taps) packed multiply-adds instead of four loads and four scalar operations.
     float *sre = smem, *sim = smem + a.span_max;
     float *str_ = smem + 2 * a.span_max, *sti = str_ + a.ntaps;
+    float2 *xs = reinterpret_cast<float2 *>(smem), *st = reinterpret_cast<float2 *>(smem + 2 * a.span_max);
     for (int t = threadIdx.x; t < a.ntaps; t += blockDim.x) {
-        str_[t] = a.taps_re[t];
-        if (CPLX) sti[t] = a.taps_im[t];
+        if (EXACT) {
+            str_[t] = a.taps_re[t];
+            if (CPLX) sti[t] = a.taps_im[t];
+        } else {
+            st[t] = make_float2(a.taps_re[t], CPLX ? a.taps_im[t] : 0.0f);
+        }
     }
     const long long j0 = (long long)blockIdx.x * a.tile;
     long long j1 = j0 + a.tile;
@@ -799,23 +807,44 @@ __global__ void __launch_bounds__(256) fir_kernel(const FirArgs a) {
     for (int s = threadIdx.x; s < span; s += blockDim.x) {
         float r, q;
         fetch<3>(a.src, k_lo + s, r, q);
-        sre[s] = r;
-        sim[s] = q;
+        if (EXACT) {
+            sre[s] = r;
+            sim[s] = q;
+        } else {
+            xs[s] = make_float2(r, q);
+        }
     }
     __syncthreads();
     for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
         const int pos = (int)(a.first + j * a.dec - k_lo);
         float ar = 0.0f, ai = 0.0f;
-        if (CPLX) {  // ComplexFirFilter.java:147-151
+        if constexpr (!EXACT) {
+            cf acc{0.0f, 0.0f};
+            const float2 *xp = xs + pos;
+            if (CPLX) {  // ComplexFirFilter.java:147-151: acc += (tr + j ti) * (xr + j xi)
+#pragma unroll 4
+                for (int t = 0; t < a.ntaps; t++) {
+                    const float2 h = st[t], x = xp[-t];
+                    acc = caxpy(h.x, cf{x.x, x.y}, acc);
+                    acc = caxpy(h.y, cf{-x.y, x.x}, acc);
+                }
+            } else if (a.real_only) {  // FirFilter.kt:141-146
+#pragma unroll 4
+                for (int t = 0; t < a.ntaps; t++) acc.x = fmaf(st[t].x, xp[-t].x, acc.x);
+            } else {  // FirFilter.kt:90-96
+#pragma unroll 4
+                for (int t = 0; t < a.ntaps; t++) {
+                    const float2 x = xp[-t];
+                    acc = caxpy(st[t].x, cf{x.x, x.y}, acc);
+                }
+            }
+            ar = acc.x;
+            ai = acc.y;
+        } else if (CPLX) {
             for (int t = 0; t < a.ntaps; t++) {
                 const float tr = str_[t], ti = sti[t], xr = sre[pos - t], xi = sim[pos - t];
-                if (EXACT) {
-                    ar = __fadd_rn(ar, __fsub_rn(__fmul_rn(tr, xr), __fmul_rn(ti, xi)));
-                    ai = __fadd_rn(ai, __fadd_rn(__fmul_rn(ti, xr), __fmul_rn(tr, xi)));
-                } else {
-                    ar += fmaf(tr, xr, -(ti * xi));
-                    ai += fmaf(ti, xr, tr * xi);
-                }
+                ar = __fadd_rn(ar, __fsub_rn(__fmul_rn(tr, xr), __fmul_rn(ti, xi)));
+                ai = __fadd_rn(ai, __fadd_rn(__fmul_rn(ti, xr), __fmul_rn(tr, xi)));
             }
         } else if (a.real_only) {  // FirFilter.kt:141-146
             for (int t = 0; t < a.ntaps; t++) ar = mac<EXACT>(ar, str_[t], sre[pos - t]);
