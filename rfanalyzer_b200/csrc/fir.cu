@@ -605,6 +605,16 @@ __device__ __forceinline__ void resample_stripe_body(const ResampleStripeArgs &s
         tile_geom(qT, rT, &k0, &sp0, &ts0);
         if (ts0) tma_load_1d(s_raw, (const char *)a.src.raw + k0 * BPS, (uint32_t)(ts0 * BPS), &s_mbar);
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int groups = (a.I + PH - 1) / PH, blocks = sa.TPC / TP;
+    static_assert(PH * TP * 2 <= 32, "one lane per reduced value");
+    // A task = PH phases x TP periods; when a tile has fewer tasks than the CTA has warps, the sample range of a task is
+    // split over `nsplit` warps and the partial sums meet in shared memory (s_acc, one float pair per output).
+    const int ntasks = groups * blocks;
+    const int nsplit = ntasks < nwarps ? nwarps / ntasks : 1;
+    float *s_acc = reinterpret_cast<float *>(smem_stripe);  // [2 * I * TPC] -- lives in front of xs (see the launcher)
+    const int task_w = warp / nsplit, part_w = warp - task_w * nsplit;
+    const int s0_w = (task_w % groups) * PH, pi0_w = (task_w / groups) * TP;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long j0 = tile * a.tile;
     long long k_al;
@@ -671,17 +681,10 @@ __device__ __forceinline__ void resample_stripe_body(const ResampleStripeArgs &s
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
         }
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int groups = (a.I + PH - 1) / PH, blocks = sa.TPC / TP;
-    static_assert(PH * TP * 2 <= 32, "one lane per reduced value");
-    // A task = PH phases x TP periods; when a tile has fewer tasks than the CTA has warps, the sample range of a task is
-    // split over `nsplit` warps and the partial sums meet in shared memory (s_acc, one float pair per output).
-    const int ntasks = groups * blocks;
-    const int nsplit = ntasks < nwarps ? nwarps / ntasks : 1;
-    float *s_acc = reinterpret_cast<float *>(smem_stripe);  // [2 * I * TPC] -- lives in front of xs (see the launcher)
     for (int sub = warp; sub < ntasks * nsplit; sub += nwarps) {
-        const int task = sub / nsplit, part = sub - task * nsplit;
-        const int s0 = (task % groups) * PH, pi0 = (task / groups) * TP;
+        // (the warp's first sub-task is the same in every tile: its divisions were done before the tile loop)
+        const int task = sub == warp ? task_w : sub / nsplit, part = sub == warp ? part_w : sub - task * nsplit;
+        const int s0 = sub == warp ? s0_w : (task % groups) * PH, pi0 = sub == warp ? pi0_w : (task / groups) * TP;
         // per phase slot: position of its newest sample in xs (period pi0) and its (padded) tap row
         int base[PH];
         const float *tapb[PH];
@@ -700,7 +703,17 @@ __device__ __forceinline__ void resample_stripe_body(const ResampleStripeArgs &s
         // aligned pair is (n-1, n) instead -- every sample of every window is still visited exactly once.
         const int n_first = (base[0] - (a.nt - 1)) & ~1, n_last = base[PH - 1] + 1;
         const int chunks = (n_last - n_first) / 64 + 1;              // 64 samples per warp step
-        const int c_lo = chunks * part / nsplit, c_hi = chunks * (part + 1) / nsplit;
+        int c_lo, c_hi;  // this warp's share of the chunks
+        if (nsplit == 1) {
+            c_lo = 0;
+            c_hi = chunks;
+        } else if (nsplit == 2) {
+            c_lo = part ? chunks >> 1 : 0;
+            c_hi = part ? chunks : chunks >> 1;
+        } else {
+            c_lo = chunks * part / nsplit;
+            c_hi = chunks * (part + 1) / nsplit;
+        }
         const float2 *xq = xs;
         for (int n = n_first + 64 * c_lo + 2 * lane; n < n_first + 64 * c_hi; n += 64) {
             float hm[PH], h0[PH], h1[PH];
