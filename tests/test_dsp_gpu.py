@@ -160,7 +160,9 @@ def test_resampler_streaming_bit_exact(gpu_ctx, oracle, i, d, maxtaps):
 
 
 @pytest.mark.parametrize("i,d,maxtaps", [(4, 25, 500), (1, 25, 500), (2, 5, 500), (6, 625, 500), (12, 625, 500), (3, 625, 500), (6, 125, 500), (12, 3125, 500),
-                                         (11, 17, 0), (17, 11, 0), (3, 2, 0), (4, 50, 500)])
+                                         (11, 17, 0), (17, 11, 0), (3, 2, 0), (4, 50, 500),
+                                         # stripe kernel corner cases: one phase (every task split six ways), more tasks than warps, odd I
+                                         (1, 400, 500), (16, 625, 500), (5, 312, 500), (7, 2000, 500)])
 def test_resampler_fast_paths_vs_oracle(gpu_ctx, oracle, i, d, maxtaps):
     """RFA_SUM_FMA selects the register-tiled kernel (taps per phase > D) or the lanes-per-output kernel:
     same counters and state as the exact kernel, samples within the demodulated-audio tolerance
