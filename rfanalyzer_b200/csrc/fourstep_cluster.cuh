@@ -68,10 +68,14 @@ struct ClusterFS {
         for (int b = 0; b < NB; b++) {
             const int i = t + b * T1;  // < 16
             const cf *xi = xa + i * CPC + col;
+            cf t[R1 - 1];  // the entries composed_twiddle reads: r = 1, 2, 3 and 4 (8, 12) -- the same products as the two-kernel path
+#pragma unroll
+            for (int r = 1; r < R1; r++)
+                if (r < 4 || (r & 3) == 0) t[r - 1] = tw1[(r - 1) * 16 + (i & 15)];
 #pragma unroll
             for (int r = 0; r < R1; r++) {
                 cf v = xi[r * STR * CPC];
-                if (r > 0) v = cmul(v, tw1[(r - 1) * 16 + (i & 15)]);
+                if (r > 0) v = cmul(v, composed_twiddle<R1>(t, r));
                 u[b * R1 + r] = v;
             }
             Dft<R1>::run(u + b * R1);
@@ -104,10 +108,14 @@ struct ClusterFS {
     static RFA_HD void b_second(const cf *xb, const cf *tw256, int row, int t, int k1, float *out, float *pk, float db_bias) {
         cf u[16];
         const cf *xi = xb + 16 * t;
+        cf tw[15];
+#pragma unroll
+        for (int r = 1; r < 16; r++)
+            if (r < 4 || (r & 3) == 0) tw[r - 1] = tw256[(r - 1) * 16 + t];
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             cf v = xi[256 * r + (row ^ r)];
-            if (r > 0) v = cmul(v, tw256[(r - 1) * 16 + t]);
+            if (r > 0) v = cmul(v, composed_twiddle<16>(tw, r));
             u[r] = v;
         }
         Dft<16>::run(u);

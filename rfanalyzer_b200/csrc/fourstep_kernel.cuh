@@ -116,7 +116,7 @@ struct FourStepA {
 #pragma unroll
             for (int r = 0; r < R1; r++) {
                 cf v = xi[r * (STR + STR / 16)];
-                if (r > 0) v = cmul(v, twreg[b * (R1 - 1) + r - 1]);
+                if (r > 0) v = cmul(v, composed_twiddle<R1>(twreg + b * (R1 - 1), r));  // R1 = 16 or 8: six (four) register twiddles per butterfly
                 u[b * R1 + r] = v;
             }
             Dft<R1>::run(u + b * R1);
@@ -152,7 +152,7 @@ struct FourStepB {
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             cf v = xi[r * 17];
-            if (r > 0) v = cmul(v, twreg[r - 1]);
+            if (r > 0) v = cmul(v, composed_twiddle<16>(twreg, r));
             u[r] = v;
         }
         Dft<16>::run(u);

@@ -418,6 +418,19 @@ RFA_HD void pass_gather(const V *x, const cf *tw, int tid, V *u) {
     }
 }
 
+// Twiddle r of a radix-R butterfly (R = 8, 16) composed from the entries a thread KEEPS: t[r-1] for r = 1, 2, 3 and
+// r = 4 (8, 12).  W^(k r) = W^(k (r & 3)) * W^(k 4 (r >> 2)): the other entries of a 15- (7-) element register array are
+// never read and the compiler drops them.  Used for the last pass's register twiddles: at N = 4096 eighteen registers
+// fewer per thread took the kernel from 43.6 to 40.5 us per 2^24 samples (profiles/r02k_composed_last_pass_twiddles.txt).
+template <int R>
+RFA_HD cf composed_twiddle(const cf *t, int r) {
+    static_assert(R == 8 || R == 16, "composition by (r & 3, r >> 2)");
+    const int lo = r & 3, hi = r >> 2;
+    if (hi == 0) return t[lo - 1];
+    if (lo == 0) return t[4 * hi - 1];
+    return cmul(t[lo - 1], t[4 * hi - 1]);
+}
+
 // Radix-32 pass with one butterfly per thread whose 31 twiddles W^(k r) are COMPOSED from ten table entries (r = 1, 2, 3
 // and r = 4, 8, ... 28) and 21 products: the last pass of the 16 x 32 x 32 plan (N = 16384) has a 127 KB table that
 // lives in L2, and 31 eight-byte loads per thread and frame with no registers to prefetch them were 27 % of that
@@ -444,6 +457,33 @@ RFA_HD void pass_gather_r32_composed(const V *x, const cf *tw, int tid, V *u) {
         u[r] = v;
     }
     Dft<R>::run(u);
+}
+
+// The same for a radix-16 pass: 15 twiddles from 6 table entries (r = 1, 2, 3 and 4, 8, 12) and 9 products
+template <int NL, int T, int P, class V>
+RFA_HD void pass_gather_r16_composed(const V *x, const cf *tw, int tid, V *u) {
+    constexpr int R = 16, E = NL / T, NB = E / R, STR = NL / R;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int i = tid + b * T;
+        const cf *twk = tw + (i & (P - 1));
+        cf lo[4], hi[4];
+#pragma unroll
+        for (int r = 1; r < 4; r++) lo[r] = twk[(r - 1) * P];
+#pragma unroll
+        for (int j = 1; j < 4; j++) hi[j] = twk[(4 * j - 1) * P];
+        const V *xi = x + phys(i);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            V v = xi[r * (STR + STR / 16)];
+            if (r > 0) {
+                const cf w = (r & 3) == 0 ? hi[r >> 2] : ((r >> 2) == 0 ? lo[r & 3] : cmul(lo[r & 3], hi[r >> 2]));
+                v = cmul(v, w);
+            }
+            u[b * R + r] = v;
+        }
+        Dft<R>::run(u + b * R);
+    }
 }
 
 // One pass, scatter side: natural-order output c of butterfly i goes to

@@ -12,6 +12,14 @@ from test_spectrum_gpu import DB_TOL, gpu_spectrum, lin_ok
 pytestmark = pytest.mark.gpu
 
 
+def same_spectra(rows, rows_d, peaks, peaks_d, avg, avg_d):
+    """Another schedule of the same transform against the default kernel.  Until round 2 these were bit-identical; the
+    default kernel now composes most of its twiddles from a few table entries (one more rounding each,
+    rfa_fft_core.cuh composed_twiddle), the experimental kernels still load all of them: equal within the tolerance."""
+    return (np.abs(rows - rows_d).max() < DB_TOL and lin_ok(rows, rows_d) and np.abs(peaks - peaks_d).max() < DB_TOL
+            and np.abs(avg - avg_d).max() < DB_TOL)
+
+
 @pytest.fixture(autouse=True)
 def _lab_knobs(gpu_ctx):
     yield
@@ -129,14 +137,14 @@ def test_fourstep_fused_producer_consumer_launch(gpu_ctx, oracle, fmt, n, frames
 @pytest.mark.parametrize("frames", [1, 2, 37, 600, 4096])
 def test_pair_kernel_is_identical_to_the_default_kernel(gpu_ctx, oracle, fmt, frames):
     """Same per-thread phase functions in another schedule (two frames per 512-thread CTA, one segment apart):
-    rows, peaks and the time average must be bit-identical to the default kernel's, for odd and even frame
+    rows, peaks and the time average must equal the default kernel's (see same_spectra), for odd and even frame
     counts, fewer and more frame pairs than SMs."""
     n = 4096
     iq = oracle.synth_iq(fmt, n * frames)
     rows_d, peaks_d, avg_d = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
     gpu_ctx.set_option("kernel", 3)
     rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
-    assert np.array_equal(rows, rows_d) and np.array_equal(peaks, peaks_d) and np.array_equal(avg, avg_d)
+    assert same_spectra(rows, rows_d, peaks, peaks_d, avg, avg_d)
     if frames <= 64:
         r, p, a = oracle.spectrum_run(fmt, iq, n, 8)
         assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL and np.abs(avg - a).max() < DB_TOL
@@ -184,13 +192,13 @@ def test_pair_kernel_ring_history_and_repeated_launches(gpu_ctx, oracle):
 @pytest.mark.parametrize("frames", [1, 2, 37, 600, 4096])
 def test_lean_kernel_is_identical_to_the_default_kernel(gpu_ctx, oracle, fmt, frames):
     """Window taps from shared memory and last-pass twiddles through L1 instead of registers, one exchange frame,
-    three CTAs per SM: the same operations in the same order, so rows, peaks and average are bit-identical."""
+    three CTAs per SM: the same transform, rows, peaks and average equal the default kernel's (see same_spectra)."""
     n = 4096
     iq = oracle.synth_iq(fmt, n * frames)
     rows_d, peaks_d, avg_d = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
     gpu_ctx.set_option("kernel", 4)
     rows, peaks, avg = gpu_spectrum(gpu_ctx, fmt, iq, n, L=8)
-    assert np.array_equal(rows, rows_d) and np.array_equal(peaks, peaks_d) and np.array_equal(avg, avg_d)
+    assert same_spectra(rows, rows_d, peaks, peaks_d, avg, avg_d)
     if frames <= 64:
         r, p, a = oracle.spectrum_run(fmt, iq, n, 8)
         assert np.abs(rows - r).max() < DB_TOL and np.abs(peaks - p).max() < DB_TOL and np.abs(avg - a).max() < DB_TOL
