@@ -422,10 +422,22 @@ RFA_HD void pass_gather(const V *x, const cf *tw, int tid, V *u) {
 // r = 4 (8, 12).  W^(k r) = W^(k (r & 3)) * W^(k 4 (r >> 2)): the other entries of a 15- (7-) element register array are
 // never read and the compiler drops them.  Used for the last pass's register twiddles: at N = 4096 eighteen registers
 // fewer per thread took the kernel from 43.6 to 40.5 us per 2^24 samples (profiles/r02k_composed_last_pass_twiddles.txt).
-template <int R>
+// KEEP = how many entries of the (R-1)-element array are read: all of them (no composition), six (four for R = 8), or
+// two (W^k and W^4k, the other powers by squaring: five more products, ten registers fewer).  Which one wins depends
+// on the kernel's register pressure: profiles/r02k_twiddles_kept_sweep.txt.
+template <int R, int KEEP = 6>
 RFA_HD cf composed_twiddle(const cf *t, int r) {
     static_assert(R == 8 || R == 16, "composition by (r & 3, r >> 2)");
+    if (KEEP >= R - 1) return t[r - 1];
     const int lo = r & 3, hi = r >> 2;
+    if (KEEP == 2) {
+        const cf l1 = t[0], l2 = cmul(l1, l1), l3 = cmul(l2, l1);
+        const cf h1 = t[3], h2 = cmul(h1, h1), h3 = cmul(h2, h1);
+        const cf L = lo == 1 ? l1 : (lo == 2 ? l2 : l3), H = hi == 1 ? h1 : (hi == 2 ? h2 : h3);
+        if (hi == 0) return L;
+        if (lo == 0) return H;
+        return cmul(L, H);
+    }
     if (hi == 0) return t[lo - 1];
     if (lo == 0) return t[4 * hi - 1];
     return cmul(t[lo - 1], t[4 * hi - 1]);

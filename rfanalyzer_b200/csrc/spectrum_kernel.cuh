@@ -136,6 +136,20 @@ struct SpectrumFrame {
     // twiddles of the last pass live in registers when there are few enough of them
     static constexpr int LAST_TW = PL::PASSES > 1 ? (E / PL::radix(LAST)) * (PL::radix(LAST) - 1) : 0;
     static constexpr bool LAST_TW_REG = LAST_TW > 0 && LAST_TW <= 16;
+    // entries of a last-pass butterfly's register twiddles that are kept (composed_twiddle)
+    // measured per size (profiles/r02k_twiddles_kept_sweep.txt, us per 2^24 samples, all / six / two kept): N = 256: 34.1 /
+    // 35.7 / 31.4, 2048: 44.1 / 41.8 / 41.1, 4096: 43.8 / 40.5 / 42.9, 128: no difference
+#ifdef RFA_TWKEEP
+    static constexpr int LAST_TW_KEEP = RFA_TWKEEP;
+#else
+    static constexpr int LAST_TW_KEEP = NL == 4096 ? 6 : 2;
+#endif
+    // radix-4 last pass (N = 64, 1024): W^2k, W^3k from the one kept W^k (1024: 41.3 -> 39.7 us, same profile file)
+#ifdef RFA_R4KEEP_ALL
+    static constexpr bool RADIX4_KEEP1 = false;
+#else
+    static constexpr bool RADIX4_KEEP1 = true;
+#endif
     // twiddle tables of the middle passes are staged in shared memory (<= 32 KB)
     static constexpr int MID_TW = PL::PASSES > 2 ? pass_tw_offset<NL>(LAST) : 0;
     static constexpr bool MID_TW_SMEM = MID_TW > 0 && MID_TW <= 4096;
@@ -268,10 +282,14 @@ struct SpectrumFrame {
                 cf v = xi[r * (STR + STR / 16)];
 #endif
                 if (r > 0) {
-                    if constexpr (R == 16 || R == 8)
-                        v = cmul(v, composed_twiddle<R>(twreg + b * (R - 1), r));
-                    else
+                    if constexpr (R == 16 || R == 8) {
+                        v = cmul(v, composed_twiddle<R, LAST_TW_KEEP>(twreg + b * (R - 1), r));
+                    } else if constexpr (R == 4 && RADIX4_KEEP1) {  // W^2k, W^3k from W^k: one kept entry per butterfly
+                        const cf w1 = twreg[b * 3], w2 = cmul(w1, w1);
+                        v = cmul(v, r == 1 ? w1 : (r == 2 ? w2 : cmul(w2, w1)));
+                    } else {
                         v = cmul(v, twreg[b * (R - 1) + r - 1]);
+                    }
                 }
                 u[b * R + r] = v;
             }
