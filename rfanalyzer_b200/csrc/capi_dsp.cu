@@ -434,6 +434,13 @@ struct rfa_chain {
     rfa_resampler *rs = nullptr;
     rfa_fir *user = nullptr, *band = nullptr, *audio1 = nullptr, *audio2 = nullptr;
     Buf fm_carry, agc_state, agc_scratch, seg;
+    Buf agc_tab;                 // fused AGC tail: double sum[2][agc_tab_npk], unsigned max key[2][agc_tab_npk], used in turn
+    long long agc_tab_npk = 0, agc_tab_used[2] = {0, 0};
+    int agc_tab_cur = 0;
+    int agc_cur = 0;             // which of the two agc_state floats holds lastMax
+    Buf seg_pin[4];              // pinned staging slots of the packet-boundary table
+    cudaEvent_t seg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long seg_calls = 0;
     DevF q_re, q_im, u_re, u_im, b_re, b_im, dem, a1, a2;
     Buf s_iq, s_audio;
     // rfa_chain_process advances the streaming state stage by stage; a failure in the middle of a call leaves
@@ -462,7 +469,11 @@ int rfa_chain_destroy(rfa_chain *ch) {
     rfa_fir_destroy(ch->band);
     rfa_fir_destroy(ch->audio1);
     rfa_fir_destroy(ch->audio2);
-    for (Buf *b : {&ch->nco, &ch->fm_carry, &ch->agc_state, &ch->agc_scratch, &ch->seg, &ch->s_iq, &ch->s_audio}) b->release();
+    for (Buf *b : {&ch->nco, &ch->fm_carry, &ch->agc_state, &ch->agc_scratch, &ch->seg, &ch->s_iq, &ch->s_audio, &ch->agc_tab}) b->release();
+    for (int i = 0; i < 4; i++) {
+        ch->seg_pin[i].release();
+        if (ch->seg_ev[i]) cudaEventDestroy(ch->seg_ev[i]);
+    }
     for (DevF *f : {&ch->q_re, &ch->q_im, &ch->u_re, &ch->u_im, &ch->b_re, &ch->b_im, &ch->dem, &ch->a1, &ch->a2}) f->b.release();
     delete ch;
     return RFA_OK;
@@ -544,9 +555,9 @@ int rfa_chain_create(rfa_ctx *c, const rfa_chain_desc *d, rfa_chain **out) {
             if ((rc = rfa_fir_create(c, t2.data(), nullptr, (int)t2.size(), 4, d->flags, &ch->audio2))) break;
         }
         if ((rc = ch->fm_carry.ensure(4 * sizeof(float)))) break;
-        if ((rc = ch->agc_state.ensure(sizeof(float)))) break;
+        if ((rc = ch->agc_state.ensure(2 * sizeof(float)))) break;
         RFA_CK(cudaMemsetAsync(ch->fm_carry.p, 0, 4 * sizeof(float), c->stream));
-        RFA_CK(cudaMemsetAsync(ch->agc_state.p, 0, sizeof(float), c->stream));
+        RFA_CK(cudaMemsetAsync(ch->agc_state.p, 0, 2 * sizeof(float), c->stream));
     } while (0);
     if (rc) {
         rfa_chain_destroy(ch);
@@ -597,7 +608,10 @@ int rfa_chain_seek(rfa_chain *ch, long long sample_index, long long *audio_index
     if (int rc = ch->rs->h.reset(c)) return rc;
     RFA_CK(cudaMemsetAsync(ch->fm_carry.p, 0, 4 * sizeof(float), c->stream));
     ch->carry_cur = 0;
-    RFA_CK(cudaMemsetAsync(ch->agc_state.p, 0, sizeof(float), c->stream));
+    RFA_CK(cudaMemsetAsync(ch->agc_state.p, 0, 2 * sizeof(float), c->stream));
+    ch->agc_cur = 0;
+    if (ch->agc_tab.p) RFA_CK(cudaMemsetAsync(ch->agc_tab.p, 0, ch->agc_tab.cap, c->stream));  // a failed call may have left maxima behind
+    ch->agc_tab_used[0] = ch->agc_tab_used[1] = 0;
     // counters: the same arithmetic rfa_chain_process applies, for sample_index inputs in one step
     const long long n = sample_index;
     ch->nco_idx = (int)(n % ch->nco_len);
@@ -784,6 +798,162 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
         guard.ok = true;
         return RFA_OK;
     }
+    // ---- AM / SSB / CW, RFA_SUM_FMA: user filter, band-pass / power, AGC and audio decimator in three launches
+    // (chain_agc.cu) plus the delay-line kernel; nothing of the call lives on the host, so a device-buffer call stays
+    // asynchronous on the context's stream like the FM modes.  RFA_SUM_EXACT keeps the separate kernels below.
+    if (!ch->exact) {
+        const bool am = mode == RFA_MODE_AM;
+        rfa_fir *u = ch->user, *b = ch->band, *f1 = ch->audio1;
+        const long long nx = am ? nu : nb;
+        const int dem_rate = am ? ch->quad_rate : ch->quad_rate / b->dec;  // ComplexFirFilter.java:167
+        const int ratio = dem_rate / kAudioRate;
+        AgcTailArgs ta{};
+        ta.q_re = ch->q_re.p();
+        ta.q_im = ch->q_im.p();
+        ta.hist_u_re = u->h.re[u->h.cur].as<float>();
+        ta.hist_u_im = u->h.im[u->h.cur].as<float>();
+        ta.user_hist = u->h.hist;
+        ta.user_taps = u->ntaps;
+        ta.taps_user = u->taps_re.as<float>();
+        ta.first_u = u->first;
+        ta.nu = nu;
+        ta.nx = nx;
+        ta.npk = (int)npk;
+        if (!am) {
+            ta.taps_b_re = b->taps_re.as<float>();
+            ta.taps_b_im = b->taps_im.as<float>();
+            ta.band_taps = b->ntaps;
+            ta.band_dec = b->dec;
+            ta.band_hist = b->h.hist;
+            ta.first_b = b->first;
+            ta.hist_b_re = b->h.re[b->h.cur].as<float>();
+            ta.hist_b_im = b->h.im[b->h.cur].as<float>();
+        }
+        if (u->dec == 1 && (ratio == 1 || ratio == 2) && (ratio == 1 || f1->ntaps <= 9) && agc_tail_supported(ta)) {
+            const long long n1 = ratio == 2 ? f1->count(nx) : 0;
+            const long long nfinal = ratio == 2 ? n1 : nx;
+            RFA_REQUIRE(nfinal <= capacity, "internal: audio count %lld exceeds capacity %lld", nfinal, capacity);
+            DevF &xbuf = am ? ch->dem : ch->b_re;
+            if (int rc = xbuf.ensure(nx)) return rc;
+            if (!am) {
+                if (int rc = ch->u_re.ensure(nu)) return rc;
+                if (int rc = ch->u_im.ensure(nu)) return rc;
+            }
+            if (int rc = ch->agc_scratch.ensure(4 * (size_t)npk * sizeof(float))) return rc;
+            {  // two per-packet tables (sum, maximum key) used in turn: all zero when (re)allocated, and the apply
+               // kernel of a call clears the one the next call fills
+                const size_t cap0 = ch->agc_tab.cap;
+                if (int rc = ch->agc_tab.ensure(2 * (size_t)npk * (sizeof(double) + sizeof(unsigned)))) return rc;
+                if (ch->agc_tab.cap != cap0) {
+                    RFA_CK(cudaMemsetAsync(ch->agc_tab.p, 0, ch->agc_tab.cap, c->stream));
+                    ch->agc_tab_npk = (long long)(ch->agc_tab.cap / (2 * (sizeof(double) + sizeof(unsigned))));
+                    ch->agc_tab_used[0] = ch->agc_tab_used[1] = 0;
+                }
+            }
+            const int tcur = ch->agc_tab_cur;
+            double *sum = ch->agc_tab.as<double>() + (size_t)tcur * ch->agc_tab_npk;
+            double *sum_next = ch->agc_tab.as<double>() + (size_t)(tcur ^ 1) * ch->agc_tab_npk;
+            unsigned *mx_base = reinterpret_cast<unsigned *>(ch->agc_tab.as<double>() + 2 * (size_t)ch->agc_tab_npk);
+            unsigned *mx_enc = mx_base + (size_t)tcur * ch->agc_tab_npk, *mx_next = mx_base + (size_t)(tcur ^ 1) * ch->agc_tab_npk;
+            // packet boundaries: through one of four pinned slots, so that neither the copy nor the call waits for the host
+            {
+                const int slot = (int)(ch->seg_calls++ & 3);
+                if (!ch->seg_ev[slot])
+                    RFA_CK(cudaEventCreateWithFlags(&ch->seg_ev[slot], cudaEventDisableTiming));
+                else
+                    RFA_CK(cudaEventSynchronize(ch->seg_ev[slot]));
+                ch->seg_pin[slot].pinned = true;
+                const size_t bytes = (size_t)(npk + 1) * sizeof(long long);
+                if (int rc = ch->seg_pin[slot].ensure(bytes)) return rc;
+                if (int rc = ch->seg.ensure(bytes)) return rc;
+                memcpy(ch->seg_pin[slot].p, (am ? u_off : b_off).data(), bytes);
+                RFA_CK(cudaMemcpyAsync(ch->seg.p, ch->seg_pin[slot].p, bytes, cudaMemcpyHostToDevice, c->stream));
+                RFA_CK(cudaEventRecord(ch->seg_ev[slot], c->stream));
+            }
+            float *d_audio = audio;
+            if (mem == RFA_MEM_HOST) {
+                if (int rc = ch->a2.ensure(nfinal)) return rc;
+                d_audio = ch->a2.p();
+            }
+            ta.u_out_re = ch->u_re.p();
+            ta.u_out_im = ch->u_im.p();
+            ta.x_out = xbuf.p();
+            ta.off = ch->seg.as<long long>();
+            ta.mx_enc = mx_enc;
+            ta.sum = sum;
+            cudaError_t e = agc_tail_launch(ta, c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "fused AGC tail kernel");
+            const float *state_in = ch->agc_state.as<float>() + ch->agc_cur;
+            float *state_out = ch->agc_state.as<float>() + (ch->agc_cur ^ 1);
+            float *gain = ch->agc_scratch.as<float>() + 2 * (size_t)npk, *mean = gain + npk;
+            const bool inl = agc_scan_is_inline((int)npk);
+            if (!inl) {
+                e = agc_scan_enc_launch(ta.off, (int)npk, sum, mx_enc, state_in, state_out, gain, mean, c->stream);
+                if (e != cudaSuccess) return cuda_fail(e, "AGC scan kernel");
+            }
+            AgcApplyArgs aa{};
+            aa.x = xbuf.p();
+            aa.nx = nx;
+            aa.off = ta.off;
+            aa.npk = (int)npk;
+            aa.scan_inline = inl ? 1 : 0;
+            aa.mx_enc = mx_enc;
+            aa.sum = sum;
+            aa.state_in = state_in;
+            aa.state_out = state_out;
+            aa.gain = gain;
+            aa.mean = mean;
+            aa.clear_mx = mx_next;
+            aa.clear_sum = sum_next;
+            aa.clear_n = (int)ch->agc_tab_used[tcur ^ 1];
+            aa.volume = ch->d.volume;
+            aa.ratio = ratio;
+            aa.taps_a1 = f1->taps_re.as<float>();
+            aa.a1_taps = f1->ntaps;
+            aa.a1_hist = f1->h.hist;
+            aa.hist_a1 = f1->h.re[f1->h.cur].as<float>();
+            aa.a1_hist_new = f1->h.re[f1->h.cur ^ 1].as<float>();
+            aa.first_a1 = f1->first;
+            aa.n1 = n1;
+            aa.audio = d_audio;
+            auto line = [&](rfa_fir *f, const float *in_re, const float *in_im, long long n) {
+                ChainStateArgs::Line &l = aa.line[aa.nlines++];
+                l.in_re = in_re;
+                l.in_im = in_im;
+                l.old_re = f->h.re[f->h.cur].as<float>();
+                l.old_im = f->h.im[f->h.cur].as<float>();
+                l.new_re = f->h.re[f->h.cur ^ 1].as<float>();
+                l.new_im = f->h.im[f->h.cur ^ 1].as<float>();
+                l.n = n;
+                l.hist = f->h.hist;
+            };
+            if (nq > 0) line(u, ch->q_re.p(), ch->q_im.p(), nq);
+            if (!am && nu > 0) line(b, ch->u_re.p(), ch->u_im.p(), nu);
+            e = agc_apply_launch(aa, am, c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "AGC apply kernel");
+            c->launches += inl ? 2 : 3;
+            ch->agc_tab_used[tcur] = npk;
+            ch->agc_tab_cur ^= 1;
+            ch->agc_cur ^= 1;
+            if (nq > 0) u->h.cur ^= 1;
+            u->first = u->first + nu * u->dec - nq;
+            if (!am) {
+                if (nu > 0) b->h.cur ^= 1;
+                b->first = b->first + nb * b->dec - nu;
+            }
+            if (ratio == 2) {
+                f1->h.cur ^= 1;  // nx > 0 here
+                f1->first = f1->first + n1 * f1->dec - nx;
+            }
+            if (mem == RFA_MEM_HOST) {
+                if (nfinal) RFA_CK(cudaMemcpyAsync(audio, d_audio, nfinal * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+                RFA_CK(cudaStreamSynchronize(c->stream));
+            }
+            *n_audio = nfinal;
+            guard.ok = true;
+            return RFA_OK;
+        }
+    }
     // ---- K5: user (channel) filter ---------------------------------------------------------------
     if (int rc = ch->u_re.ensure(nu)) return rc;
     if (int rc = ch->u_im.ensure(nu)) return rc;
@@ -813,7 +983,7 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
         cudaError_t e = demod_power_launch(ch->u_re.p(), ch->u_im.p(), nu, ch->dem.p(), c->num_sms, c->stream);
         if (e == cudaSuccess)
             e = agc_launch(ch->dem.p(), ch->seg.as<long long>(), (int)npk, max_segment(u_off), true,
-                           ch->agc_state.as<float>(), ch->agc_scratch.as<float>(), volume, ch->exact, c->num_sms, c->stream);
+                           ch->agc_state.as<float>() + ch->agc_cur, ch->agc_scratch.as<float>(), volume, ch->exact, c->num_sms, c->stream);
         if (e != cudaSuccess) return cuda_fail(e, "am kernels");
         c->launches += 4;
         dem = ch->dem.p();
@@ -828,7 +998,7 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
         if (int rc = fir_run(ch->band, in, nu, false, ch->b_re.p(), ch->b_im.p(), nb, nullptr, nullptr)) return rc;
         if (int rc = upload_segments(b_off)) return rc;
         cudaError_t e = agc_launch(ch->b_re.p(), ch->seg.as<long long>(), (int)npk, max_segment(b_off), false,
-                                   ch->agc_state.as<float>(), ch->agc_scratch.as<float>(), volume, ch->exact, c->num_sms,
+                                   ch->agc_state.as<float>() + ch->agc_cur, ch->agc_scratch.as<float>(), volume, ch->exact, c->num_sms,
                                    c->stream);
         if (e != cudaSuccess) return cuda_fail(e, "agc kernels");
         c->launches += 3;

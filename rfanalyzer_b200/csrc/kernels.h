@@ -65,6 +65,57 @@ struct ChainStateArgs {
 };
 cudaError_t chain_state_launch(const ChainStateArgs &a, cudaStream_t st);
 
+// everything behind the resampler of an AM / SSB / CW chain in three launches (chain_agc.cu, RFA_SUM_FMA)
+struct AgcTailArgs {
+    const float *q_re, *q_im;              // quadrature samples of this call
+    const float *hist_u_re, *hist_u_im;    // user filter delay line
+    int user_hist, user_taps;
+    const float *taps_user;
+    long long first_u, nu;                 // as FmTailArgs
+    const float *taps_b_re, *taps_b_im;    // complex band-pass (band_taps == 0: AM, x = re^2 + im^2 of the user filter's output)
+    int band_taps, band_dec, band_hist;
+    long long first_b;
+    const float *hist_b_re, *hist_b_im;    // band-pass delay line (user-filter outputs of earlier calls)
+    float *u_out_re, *u_out_im;            // [nu] user-filter outputs; only the last band_hist are written (the next delay line)
+    long long nx;                          // demodulated samples of this call (band-pass outputs, or nu)
+    float *x_out;                          // [nx] demodulated samples before the AGC
+    const long long *off;                  // [npk + 1] packet boundaries in the demodulated stream
+    int npk;
+    unsigned *mx_enc;                      // [npk] per-packet maximum as an ordered key, 0 = cleared
+    double *sum;                           // [npk] per-packet sum (AM), cleared
+};
+bool agc_tail_supported(const AgcTailArgs &a);
+cudaError_t agc_tail_launch(const AgcTailArgs &a, cudaStream_t st);
+bool agc_scan_is_inline(int npk);  // few enough packets for the apply kernel's CTAs to run the AGC recurrence themselves
+cudaError_t agc_scan_enc_launch(const long long *off, int npk, const double *sum, const unsigned *mx_enc, const float *state_in,
+                                float *state_out, float *gain, float *mean, cudaStream_t st);
+struct AgcApplyArgs {
+    const float *x;                        // [nx] demodulated samples
+    long long nx;
+    const long long *off;
+    int npk;
+    int scan_inline;                       // 1: gains from mx_enc / sum / state_in in the kernel; 0: from gain / mean
+    const unsigned *mx_enc;
+    const double *sum;
+    const float *state_in;                 // [1] lastMax before this call
+    float *state_out;                      // [1] after it (scan_inline)
+    const float *gain, *mean;              // [npk] (scan kernel's output)
+    unsigned *clear_mx;                    // the packet table of the NEXT call: cleared here
+    double *clear_sum;
+    int clear_n;
+    float volume;
+    int ratio;                             // demodulated rate / 48 kHz: 1 or 2
+    const float *taps_a1;                  // ratio 2: first audio decimator
+    int a1_taps, a1_hist;
+    const float *hist_a1;
+    float *a1_hist_new;                    // ratio 2: the decimator's delay line after this call
+    long long first_a1, n1;
+    float *audio;
+    int nlines;                            // delay lines slid by extra CTAs (user filter, band-pass)
+    ChainStateArgs::Line line[2];
+};
+cudaError_t agc_apply_launch(const AgcApplyArgs &a, bool subtract_mean, cudaStream_t st);
+
 // waterfall / trace preprocessing (render.cu); viewport scalars are computed by the caller (capi.cu)
 struct RenderDesc {
     const float *rows = nullptr;

@@ -307,6 +307,38 @@ def test_chain_streams_across_calls(gpu_ctx, oracle):
     assert np.array_equal(np.concatenate([b1[:n1], b2[:n2]]), a[:na])
 
 
+@pytest.mark.parametrize("fmt,fs,mode,width,packet,calls", [
+    (2, 10_000_000, 5, 2_800, 65536, (3, 1, 4)),       # USB: band-pass /2, three calls
+    (2, 10_000_000, 6, 300, 65536, (2, 5, 1)),         # CW: band-pass /1
+    (2, 10_000_000, 1, 8_000, 65536, (4, 1, 3)),       # AM: power, audio decimator
+    (1, 2_400_000, 1, 8_000, 64, (2, 30, 1, 50)),      # AM, calls shorter than the audio decimator's delay line
+    (1, 2_400_000, 4, 2_800, 64, (2, 30, 1, 50)),      # LSB, a handful of samples per packet
+    (1, 2_400_000, 5, 2_800, 512, (1100, 3)),          # USB, more packets than the in-kernel AGC scan takes
+])
+def test_fused_agc_tail_streams_across_calls(gpu_ctx, oracle, fmt, fs, mode, width, packet, calls):
+    """RFA_SUM_FMA runs AM / SSB / CW behind the resampler in the fused kernels of chain_agc.cu: delay lines of the
+    user filter, band-pass and audio decimator, the AGC maximum and the two alternating packet tables carry from call
+    to call -- several calls of uneven length equal the oracle's single run (BASELINE tolerance for audio)."""
+    import rfanalyzer_b200 as rfa
+    n = packet * sum(calls)
+    iq, src, chan = _chain_input(oracle, rfa, fmt, fs, mode, n)
+    want = oracle.chain_run(fmt, iq, fs, src, chan, mode, width, packet, volume=0.8)
+    plan = rfa.ChainPlan(gpu_ctx, fmt, fs, src, chan, mode, width, packet, 0.8, rfa.SUM_FMA)
+    bps = 2 if fmt < 2 else 4
+    got, pos = [], 0
+    for k in calls:
+        m = packet * k
+        audio = np.zeros(plan.max_audio(m), np.float32)
+        cnt = plan.process(iq[pos * bps:(pos + m) * bps], m, audio)
+        got.append(audio[:cnt])
+        pos += m
+    got = np.concatenate(got)
+    assert len(got) == len(want)
+    ok = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), ok) and ok.sum() > len(want) // 2
+    assert np.abs(got[ok] - want[ok]).max() <= 1e-4 * np.abs(want[ok]).max()
+
+
 def test_chain_device_buffers(gpu_ctx, oracle):
     import torch
     import rfanalyzer_b200 as rfa
