@@ -416,6 +416,85 @@ def recording_strong_scaling(torch, dist, rfa, ctx, stream, plan, shard_cls, ran
     return float(ms.item()) * 1e-3, log2_total, calls, ok
 
 
+def chain_strong_scaling(torch, dist, rfa, ctx, stream, rank, world, log2_total=29):
+    """BASELINE config 4 over the box: ONE Airspy int16 recording of 2^log2_total samples @10 Msps, time-sharded by
+    whole packets with a warm-up halo (rfanalyzer_b200.sharding.ShardedChain: seek to a packet boundary, re-process the
+    halo, discard its audio; no data-path collective), nFM and USB.  The run checks itself: every rank's audio is
+    gathered on rank 0 and compared with the sequential single-GPU run of the whole recording computed there --
+    FM bit for bit, USB (the AGC maximum decays by 0.95 per packet over a 256-packet halo) to 1e-4 of the peak."""
+    from rfanalyzer_b200.sharding import ShardedChain
+    fs, packet, total = 10_000_000, 65536, 1 << log2_total
+    off = fs // 10
+    out = {}
+    for name, mode, width in (("nfm", rfa.MODE_NFM, 10_000), ("usb", rfa.MODE_USB, 2_800)):
+        comps = [(rfa.synth_step(off / fs), 60 * 256, rfa.synth_step(1000 / fs), 3_130_000 if mode == rfa.MODE_NFM else 0),
+                 (rfa.synth_step((off + 1200) / fs), 20 * 256, 0, 0)]
+        with torch.cuda.stream(stream):
+            plan = rfa.ChainPlan(ctx, rfa.FMT_S16LE, fs, 100_000_000, 100_000_000 + off, mode, width, packet, 1.0, rfa.SUM_FMA)
+            sc = ShardedChain(plan, rank, world)
+            halo_start, first, n = sc.segment(total)
+            mine = first + n - halo_start
+            iq = torch.empty(mine * 4, dtype=torch.uint8, device="cuda")
+            rfa.synth_iq(ctx, rfa.FMT_S16LE, mine, iq, first=halo_start, comps=comps, noise_shift=3)
+            audio = torch.zeros(plan.max_audio(max(n, first - halo_start, 1)), dtype=torch.float32, device="cuda")
+            sc.process(iq, total, audio)  # warm
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            index, got = sc.process(iq, total, audio)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            meta = torch.tensor([index, got], dtype=torch.int64, device="cuda")
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                metas = [torch.zeros_like(meta) for _ in range(world)]
+                dist.all_gather(metas, meta)
+                cap = int(max(int(m[1]) for m in metas))
+                padded = torch.zeros(cap, dtype=torch.float32, device="cuda")
+                padded[:got] = audio[:got]
+                pieces = [torch.zeros_like(padded) for _ in range(world)] if rank == 0 else None
+                dist.gather(padded, pieces, dst=0)
+            else:
+                metas, pieces = [meta], [audio[:got].clone()]
+            ok, detail = True, None
+            if rank == 0:
+                del iq
+                whole = torch.empty(total * 4, dtype=torch.uint8, device="cuda")
+                rfa.synth_iq(ctx, rfa.FMT_S16LE, total, whole, comps=comps, noise_shift=3)
+                seq = rfa.ChainPlan(ctx, rfa.FMT_S16LE, fs, 100_000_000, 100_000_000 + off, mode, width, packet, 1.0, rfa.SUM_FMA)
+                want = torch.zeros(seq.max_audio(total), dtype=torch.float32, device="cuda")
+                nw = seq.process(whole, total, want)
+                stream.synchronize()
+                pos = 0
+                worst = 0.0
+                peak = float(want[:nw].abs().max().item())
+                for r in range(world):
+                    idx, cnt = int(metas[r][0]), int(metas[r][1])
+                    ok = ok and idx == pos
+                    a, b = pieces[r][:cnt], want[idx:idx + cnt]
+                    if mode == rfa.MODE_NFM:
+                        ok = ok and bool(torch.equal(a, b))
+                    elif cnt:
+                        worst = max(worst, float((a - b).abs().max().item()))
+                    pos += cnt
+                ok = ok and pos == nw and (mode == rfa.MODE_NFM or worst <= 1e-4 * peak)
+                detail = "bit-identical to the sequential run" if mode == rfa.MODE_NFM else "max |diff| %.2e of peak" % (worst / peak if peak else 0.0)
+                seq.close()
+                del whole, want
+            plan.close()
+            secs = float(ms.item()) * 1e-3
+            out[name] = {"Msamples_per_s": total / secs / 1e6, "seconds": secs, "halo_packets": sc.halo_packets,
+                         "audio_samples": int(sum(int(m[1]) for m in metas)), "equals_sequential_run": bool(ok), "check": detail}
+        torch.cuda.empty_cache()
+    return {"workload": "BASELINE config 4 over the box: ONE Airspy int16 recording of 2^%d samples @10 Msps time-sharded over %d "
+                        "GPU(s) by whole packets with a warm-up halo, no data-path collective; device-timed, max over ranks"
+                        % (log2_total, world), "n_gpus": world, "scaling": "strong", **out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -633,6 +712,15 @@ def main():
         except Exception as e:  # never lose the headline over the secondary measurement
             recording = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
+    chain_rec = None
+    if not args.no_configs:
+        try:
+            chain_rec = chain_strong_scaling(torch, dist, rfa, ctx, stream, rank, world)
+            if rank == 0:
+                verified = verified and all(v["equals_sequential_run"] for v in chain_rec.values() if isinstance(v, dict))
+        except Exception as e:
+            chain_rec = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_configs:
         try:
             configs = other_configs(torch, rfa, ctx, stream, peak_gbs, not args.no_cpu_baseline)
@@ -677,6 +765,8 @@ def main():
             out["recording"] = recording
         if configs is not None:
             out["configs"] = configs
+        if chain_rec is not None:
+            out["chain_recording"] = chain_rec
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import oracle as O

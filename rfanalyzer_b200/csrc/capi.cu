@@ -682,17 +682,18 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
     const size_t frame_in = (size_t)n * bps, frame_out = (size_t)n * sizeof(float);
     // IQ bytes per chunk: small enough that the first copy in and the last copy out (which overlap with
     // nothing) are short, large enough that the per-chunk launch and copy set-up costs stay hidden
-    const size_t chunk_bytes = (size_t)c->tune.chunk_kib << 10;  // knob "chunk_kib", default 4 MiB
+    const size_t chunk_bytes = (size_t)c->tune.chunk_kib << 10;  // knob "chunk_kib", default 8 MiB
     long long cf_frames = (long long)(chunk_bytes / frame_in);
     if (cf_frames < L + 1) cf_frames = L + 1;
     if (cf_frames > nframes) cf_frames = nframes;
     // chunk schedule: a SHORT first chunk (an eighth), so that the copy out -- the engine that bounds this path: 4 bytes
-    // of rows leave per 2 bytes of IQ -- starts after 15 us instead of 90; whole chunks; the last one takes the remainder
+    // of rows leave per 2 bytes of IQ -- starts after 15 us instead of 90
     std::vector<long long> sizes;
     {
         long long left = nframes;
         long long first = cf_frames / 8;
         if (first < L + 1) first = L + 1;
+#ifdef RFA_NO_RAMP  // timing build: round 2's earlier schedule (one short chunk, whole chunks, the remainder)
         if (left >= first + 2 * cf_frames) {
             sizes.push_back(first);
             left -= first;
@@ -702,6 +703,28 @@ int rfa_spectrum_process(rfa_spectrum_plan *pl, const void *iq, long long nframe
             left -= cf_frames;
         }
         sizes.push_back(left);
+        left = 0;
+#endif
+        if (left >= first + 2 * cf_frames) {
+            // ... and a ramp behind it: while a chunk's rows leave (4 bytes per 2 bytes of IQ), the next chunk's IQ must
+            // arrive and be transformed, or the copy-out engine idles -- after an eighth-size chunk a full-size one takes
+            // four times as long to come in as the small one's rows take to leave.  Growth by 3/2 keeps it fed.
+            long long sz = first;
+            while (sz < cf_frames && left >= sz + 2 * cf_frames) {
+                sizes.push_back(sz);
+                left -= sz;
+                sz += (sz + 1) / 2;
+            }
+        }
+        // the rest in equal chunks of at most cf_frames (a long last chunk would starve the copy-out engine while it comes in)
+        long long nrest = left > 0 ? (left + cf_frames - 1) / cf_frames : 0;
+        while (nrest > 1 && left / nrest < L + 1) nrest--;
+        for (long long i = 0; i < nrest; i++) {
+            const long long take = left / (nrest - i);
+            sizes.push_back(take);
+            left -= take;
+        }
+        if (sizes.empty()) sizes.push_back(left);
     }
     const long long nchunks = (long long)sizes.size();
     long long max_chunk = 0;

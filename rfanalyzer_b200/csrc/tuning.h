@@ -16,7 +16,7 @@ struct Tuning {
     int fs_tma = 1;              // "fs_tma": four-step column kernel loads raw IQ as 2-D tensor-map boxes
     int fs_ztma = 1;             // "fs_ztma": ... and stores the intermediate as one tensor-map store per frame
     int fs_pdl = 1;              // "fs_pdl": four-step kernels chained by programmatic dependent launch
-    int chunk_kib = 4096;        // "chunk_kib": IQ bytes per chunk of the host-buffer H2D -> kernel -> D2H pipeline
+    int chunk_kib = 8192;        // "chunk_kib": IQ bytes per chunk of the host-buffer H2D -> kernel -> D2H pipeline
     int rs_span = 0;             // "rs_span": samples staged per CTA by the tiled resampler, 0 = default
     // "cluster": N >= 32768 on thread-block clusters, the four-step intermediate in distributed shared memory
     // (fourstep_cluster.cuh): ONE launch and a third of the two-kernel path's HBM traffic, but measured 119 / 93 us

@@ -10,7 +10,7 @@ plan = rfa.SpectrumPlan(ctx, rfa.FMT_S8, N, avg_len=8)
 iq = torch.empty(S * 2, dtype=torch.uint8).pin_memory(); iq.random_(0, 255)
 rows = torch.empty((F, N), dtype=torch.float32).pin_memory()
 peaks = torch.empty(N, dtype=torch.float32).pin_memory(); avg = torch.empty(N, dtype=torch.float32).pin_memory()
-for kib in (2048, 4096, 8192, 16384, 4096, 8192):
+for kib in [int(k) for k in os.environ.get("KIBS", "2048,4096,8192,16384,4096,8192").split(",")]:
     ctx.set_option("chunk_kib", kib)
     for _ in range(3):
         plan.process(iq.numpy(), F, rows=rows.numpy(), peaks=peaks.numpy(), avg=avg.numpy())
