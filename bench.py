@@ -420,8 +420,11 @@ def chain_strong_scaling(torch, dist, rfa, ctx, stream, rank, world, log2_total=
     """BASELINE config 4 over the box: ONE Airspy int16 recording of 2^log2_total samples @10 Msps, time-sharded by
     whole packets with a warm-up halo (rfanalyzer_b200.sharding.ShardedChain: seek to a packet boundary, re-process the
     halo, discard its audio; no data-path collective), nFM and USB.  The run checks itself: every rank's audio is
-    gathered on rank 0 and compared with the sequential single-GPU run of the whole recording computed there --
-    FM bit for bit, USB (the AGC maximum decays by 0.95 per packet over a 256-packet halo) to 1e-4 of the peak."""
+    gathered on rank 0 and compared with the sequential single-GPU run of the whole recording computed there, to
+    BASELINE's tolerance for audio (1e-4 of the peak).  The delay lines are exact after the halo, but the stripe
+    resampler's summation order per output depends on where its tiles fall in the call (which outputs share a warp
+    task, how a task's sample range is split), so a rank's bits equal the sequential run's only when its segment starts
+    on a tile boundary; the AGC maximum of USB decays by 0.95 per packet over the 256-packet halo."""
     from rfanalyzer_b200.sharding import ShardedChain
     fs, packet, total = 10_000_000, 65536, 1 << log2_total
     off = fs // 10
@@ -471,18 +474,18 @@ def chain_strong_scaling(torch, dist, rfa, ctx, stream, rank, world, log2_total=
                 stream.synchronize()
                 pos = 0
                 worst = 0.0
+                identical = True
                 peak = float(want[:nw].abs().max().item())
                 for r in range(world):
                     idx, cnt = int(metas[r][0]), int(metas[r][1])
                     ok = ok and idx == pos
                     a, b = pieces[r][:cnt], want[idx:idx + cnt]
-                    if mode == rfa.MODE_NFM:
-                        ok = ok and bool(torch.equal(a, b))
-                    elif cnt:
+                    identical = identical and bool(torch.equal(a, b))
+                    if cnt:
                         worst = max(worst, float((a - b).abs().max().item()))
                     pos += cnt
-                ok = ok and pos == nw and (mode == rfa.MODE_NFM or worst <= 1e-4 * peak)
-                detail = "bit-identical to the sequential run" if mode == rfa.MODE_NFM else "max |diff| %.2e of peak" % (worst / peak if peak else 0.0)
+                ok = ok and pos == nw and worst <= 1e-4 * peak
+                detail = "max |diff| %.2e of peak%s" % (worst / peak if peak else 0.0, ", bit-identical" if identical else "")
                 seq.close()
                 del whole, want
             plan.close()
