@@ -302,7 +302,10 @@ int rfa_mode_info(int mode, int *quadrature_rate, int *min_width, int *max_width
 /* ---- the whole IQ -> audio chain ------------------------------------------------------------
  * Scheduler.kt:237-244 (mixPacketIntoSamplePacket) -> Resampler.kt:95-113 -> Demodulator.kt:147-187
  * (user filter, demodulator, volume) -> AudioSink.java:182-187 (decimation to 48 kHz), every packet
- * delivered.  State carries across calls; every call but the last must be a whole number of packets. */
+ * delivered.  State carries across calls; every call but the last must be a whole number of packets.
+ * RFA_MEM_HOST calls return with the audio in the caller's buffer.  RFA_MEM_DEVICE calls of RFA_SUM_FMA chains only
+ * enqueue work on the context's stream (*n_audio is known on return, the samples are there after rfa_ctx_sync or any
+ * later work on that stream); RFA_SUM_EXACT AM / SSB / CW calls synchronise before they return. */
 typedef struct {
     int format;                  /* RFA_FMT_* */
     int sample_rate;             /* source sample rate, Hz */
