@@ -52,8 +52,18 @@ __device__ __forceinline__ float dec_max(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-// largest p with off[p] <= i (off[0] = 0, off[npk] > i); empty packets are stepped over
+// largest p with off[p] <= i (off[0] = 0, off[npk] > i); empty packets are stepped over.  Packets are (nearly) equal in
+// length, so the proportional guess is right or one off almost always: its three neighbouring boundaries are loaded at once
+// and only a miss pays for the binary search's chain of dependent loads.
 __device__ __forceinline__ int find_packet(const long long *__restrict__ off, int npk, long long i) {
+    const long long total = __ldg(off + npk);
+    int g = total > 0 ? (int)((double)i * (double)npk / (double)total) : 0;
+    g = g < 1 ? 1 : (g > npk - 1 ? npk - 1 : g);
+    if (npk >= 2) {
+        const long long o0 = __ldg(off + g - 1), o1 = __ldg(off + g), o2 = __ldg(off + g + 1);
+        if (o1 <= i && i < o2) return g;
+        if (o0 <= i && i < o1 && o0 < o1) return g - 1;
+    }
     int lo = 0, hi = npk;  // off[lo] <= i < off[hi]
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -99,6 +109,8 @@ __global__ void __launch_bounds__(256) agc_tail_kernel(const AgcTailArgs a) {
     if (x1 > a.nx) x1 = a.nx;
     if (x0 >= x1) return;
     const bool last_cta = x1 == a.nx;
+    __shared__ int s_plo;  // packet of the CTA's first sample: looked up now, its loads overlap the staging
+    if (threadIdx.x == 255) s_plo = find_packet(a.off, a.npk, x0);
     for (int t = threadIdx.x; t < UT; t += blockDim.x) s_tu[t] = t < a.user_taps ? a.taps_user[t] : 0.0f;
     if (threadIdx.x < 8) smem_tail[threadIdx.x] = make_float2(0.0f, 0.0f);
     if (BAND) {
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(256) agc_tail_kernel(const AgcTailArgs a) {
     // ---- demodulated samples out, per-packet maximum (and sum) ----
     for (int j = threadIdx.x; j < nxs; j += blockDim.x) a.x_out[x0 + j] = s_x[j];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int p_lo = find_packet(a.off, a.npk, x0);
+    const int p_lo = s_plo;
     for (int p = p_lo + warp; p < a.npk; p += 8) {
         const long long b = __ldg(a.off + p), e = __ldg(a.off + p + 1);
         if (b >= x1) break;
@@ -326,6 +338,15 @@ __global__ void __launch_bounds__(256) agc_apply_kernel(const AgcApplyArgs a) {
     const long long c0 = (long long)blockIdx.x * CT;
     long long c1 = c0 + CT;
     if (c1 > a.nx) c1 = a.nx;
+    // this thread's demodulated samples: loaded now, so that their latency hides behind the packet search and the scan
+    constexpr int XPT = (CT + A1T + 255) / 256;
+    const long long x_lo = c0 - (RATIO == 2 ? a.a1_taps - 1 : 0);  // RATIO 2: s_y[0]
+    float xv[XPT];
+#pragma unroll
+    for (int k = 0; k < XPT; k++) {
+        const long long i = x_lo + threadIdx.x + 256 * k;
+        xv[k] = (i >= 0 && i < c1) ? __ldg(a.x + i) : 0.0f;
+    }
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < a.clear_n; i += blockDim.x) {
             a.clear_mx[i] = 0u;
@@ -388,24 +409,29 @@ __global__ void __launch_bounds__(256) agc_apply_kernel(const AgcApplyArgs a) {
         }
         return lo;
     };
-    auto normalised = [&](long long i) {
+    auto normalised = [&](long long i, float v) {
         const int p = packet_of(i);
-        float v = a.x[i];
         if (SUBTRACT_MEAN) v = __fsub_rn(v, mean[p]);
         return __fmul_rn(__fmul_rn(v, gain[p]), a.volume);
     };
     if (RATIO == 1) {
-        for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) a.audio[i] = normalised(i);
+#pragma unroll
+        for (int k = 0; k < XPT; k++) {
+            const long long i = x_lo + threadIdx.x + 256 * k;
+            if (i < c1) a.audio[i] = normalised(i, xv[k]);
+        }
         return;
     }
     if (threadIdx.x < A1T) s_t1[threadIdx.x] = threadIdx.x < a.a1_taps ? a.taps_a1[threadIdx.x] : 0.0f;
-    const int halo = a.a1_taps - 1;
-    const long long lo = c0 - halo;  // s_y[0]
-    for (int s = threadIdx.x; s < (int)(c1 - lo); s += blockDim.x) {
+    const long long lo = x_lo;  // s_y[0]
+#pragma unroll
+    for (int k = 0; k < XPT; k++) {
+        const int s = threadIdx.x + 256 * k;
         const long long i = lo + s;
+        if (i >= c1) continue;
         float y = 0.0f;
         if (i >= 0) {
-            y = normalised(i);
+            y = normalised(i, xv[k]);
             if (i >= c0 && i >= a.nx - a.a1_hist) a.a1_hist_new[i - (a.nx - a.a1_hist)] = y;  // the decimator's next delay line
         } else if (i + a.a1_hist >= 0) {
             y = a.hist_a1[i + a.a1_hist];
