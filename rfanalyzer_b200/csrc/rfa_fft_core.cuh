@@ -345,6 +345,11 @@ RFA_CX int plan_passes(int lg) { return lg == 12 ? 4 : (lg == 14 ? 3 : lg / 4 + 
 RFA_CX int plan_radix(int lg, int pass) {
     return lg == 12 ? 8 : (lg == 14 ? (pass == 0 ? 16 : 32) : (pass < lg / 4 ? 16 : (1 << (lg % 4))));
 }
+#elif defined(RFA_E32_8192)  // timing experiment: N = 8192 as 16 x 16 x 32 with 32 points per thread (256 threads per frame, two CTAs per SM)
+RFA_CX int plan_passes(int lg) { return (lg == 14 || lg == 13) ? 3 : lg / 4 + (lg % 4 ? 1 : 0); }
+RFA_CX int plan_radix(int lg, int pass) {
+    return lg == 14 ? (pass == 0 ? 16 : 32) : (lg == 13 ? (pass < 2 ? 16 : 32) : (pass < lg / 4 ? 16 : (1 << (lg % 4))));
+}
 #else
 RFA_CX int plan_passes(int lg) { return lg == 14 ? 3 : lg / 4 + (lg % 4 ? 1 : 0); }
 RFA_CX int plan_radix(int lg, int pass) {

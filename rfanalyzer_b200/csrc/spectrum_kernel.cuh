@@ -58,6 +58,8 @@ template <int NL>
 struct Geom {
 #ifdef RFA_R8
     static constexpr int T = NL == 4096 ? 512 : (NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1)));
+#elif defined(RFA_E32_8192)
+    static constexpr int T = NL == 8192 ? 256 : (NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1)));
 #else
     static constexpr int T = NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1));
 #endif
@@ -65,7 +67,11 @@ struct Geom {
     static constexpr int FPC = T >= 256 ? 1 : 256 / T;   // frames per CTA
     static constexpr int CTA = T * FPC;
     // two ping-pong frames per slot (one barrier per pass) while they fit comfortably
+#ifdef RFA_E32_8192
+    static constexpr int NBUF = NL < 8192 ? 2 : 1;
+#else
     static constexpr int NBUF = NL <= 8192 ? 2 : 1;
+#endif
     static constexpr size_t SMEM = (size_t)FPC * NBUF * Plan<NL>::SMEM_POINTS * sizeof(cf);
 };
 
@@ -518,6 +524,17 @@ __device__ __forceinline__ float average_row_term(const SpectrumParams &p, int r
     return __ldcg(p.rows + row * p.row_stride + i);
 }
 __device__ __forceinline__ void average_cta(const SpectrumParams &p, int S, int N, int n_tail) {
+    // where the newest avg_len+1 rows start: once per CTA (a 64-bit modulo per row and bin made this CTA the launch's
+    // last one to finish at 8192 points on 256 threads -- 32 trips of nine dependent address chains and an L2 round trip)
+    __shared__ long long s_row_off[31];
+    if (threadIdx.x < 31) {
+        long long row = p.avg_newest + (long long)threadIdx.x * p.avg_dir;
+        if (p.ring_rows > 0) {
+            row %= p.ring_rows;
+            if (row < 0) row += p.ring_rows;
+        }
+        s_row_off[threadIdx.x] = row * p.row_stride;
+    }
     if (threadIdx.x == 0) {
         for (int c = 0; c < S; c++) {
             volatile unsigned int *t = p.ticket + TICKET_TAIL + c;
@@ -526,19 +543,31 @@ __device__ __forceinline__ void average_cta(const SpectrumParams &p, int S, int 
     }
     __syncthreads();
     __threadfence();  // the workers' rows, published before their counts
+    const int nr = p.avg_len + 1 < 31 ? p.avg_len + 1 : 31;
+    const float inv_terms = (float)(p.avg_len + 1);
+    // two bins per trip: twice the loads in flight per L2 round trip
 #pragma unroll 1
-    for (int i = (int)threadIdx.x; i < N; i += (int)blockDim.x) {
-        float v[31];
+    for (int i0 = (int)threadIdx.x; i0 < N; i0 += 2 * (int)blockDim.x) {
+        const int i1 = i0 + (int)blockDim.x;
+        float v0[31], v1[31];
 #pragma unroll
         for (int r = 0; r < 31; r++) {
-            v[r] = -9999.0f;
-            if (r <= p.avg_len && r < p.avg_valid) v[r] = average_row_term(p, r, i);
+            v0[r] = v1[r] = -9999.0f;
+            if (r < nr && r < p.avg_valid) {
+                const float *row = p.rows + s_row_off[r];
+                v0[r] = __ldcg(row + i0);
+                if (i1 < N) v1[r] = __ldcg(row + i1);
+            }
         }
-        float sum = 0.0f;
+        float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
         for (int r = 0; r < 31; r++)
-            if (r <= p.avg_len) sum = __fadd_rn(sum, v[r]);
-        p.avg[i] = __fdiv_rn(sum, (float)(p.avg_len + 1));
+            if (r < nr) {
+                sum0 = __fadd_rn(sum0, v0[r]);
+                sum1 = __fadd_rn(sum1, v1[r]);
+            }
+        p.avg[i0] = __fdiv_rn(sum0, inv_terms);
+        if (i1 < N) p.avg[i1] = __fdiv_rn(sum1, inv_terms);
     }
 }
 
