@@ -142,14 +142,20 @@ static int resampler_run(rfa_resampler *r, StreamDesc in, long long n, float *ou
     long long nout = r->count(n);
     if (nout > capacity) nout = capacity;
     r->h.attach(in);
-    cudaError_t e = resample_launch(in, r->bank.as<float>(), r->I, r->D, r->nt, r->rel, r->ph, nout, out_re, out_im,
-                                    r->exact, c->stream, c->tune.rs_span);
-    if (e != cudaSuccess) return cuda_fail(e, "resample kernel");
-    if (nout > 0) c->launches++;
     const long long T = (long long)r->ph + nout * r->D;
     const long long kk = r->rel + T / r->I;  // where the next output will be computed
     const long long cons = kk < n ? kk : n;  // RationalResampler.kt:136-149
-    if (int rc = r->h.advance(c, in, cons)) return rc;
+    bool hist_done = false;  // the tiled / stripe kernels slide the delay line themselves (CTA 0, before its tiles)
+    cudaError_t e = resample_launch(in, r->bank.as<float>(), r->I, r->D, r->nt, r->rel, r->ph, nout, out_re, out_im,
+                                    r->exact, c->stream, c->tune.rs_span, r->h.re[r->h.cur ^ 1].as<float>(),
+                                    r->h.im[r->h.cur ^ 1].as<float>(), cons, &hist_done);
+    if (e != cudaSuccess) return cuda_fail(e, "resample kernel");
+    if (nout > 0) c->launches++;
+    if (hist_done) {
+        r->h.cur ^= 1;
+    } else if (int rc = r->h.advance(c, in, cons)) {
+        return rc;
+    }
     r->rel = kk - cons;
     r->ph = (int)(T % r->I);
     if (n_out) *n_out = nout;
@@ -754,30 +760,53 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
         fa.first_a2 = f2->first;
         fa.n1 = n1;
         fa.n2 = n2;
-        fa.dem_out = ch->dem.p();
-        fa.a1_out = ch->a1.p();
         fa.audio = d_audio;
+        // the delay lines slide inside the same launch (an extra CTA for the user filter, the owning CTAs for the
+        // decimators); nothing else needs the demodulated stream or the first decimator's output in global memory
+        const bool fused_state = nu > 0;
+        if (fused_state) {
+            fa.dem_out = nullptr;
+            fa.a1_out = nullptr;
+            if (nq > 0) {
+                fa.slide_user = 1;
+                ChainStateArgs::Line &l = fa.user_line;
+                l.in_re = ch->q_re.p();
+                l.in_im = ch->q_im.p();
+                l.old_re = u->h.re[u->h.cur].as<float>();
+                l.old_im = u->h.im[u->h.cur].as<float>();
+                l.new_re = u->h.re[u->h.cur ^ 1].as<float>();
+                l.new_im = u->h.im[u->h.cur ^ 1].as<float>();
+                l.n = nq;
+                l.hist = u->h.hist;
+            }
+            if (ratio >= 2) fa.a1_hist_new = f1->h.re[f1->h.cur ^ 1].as<float>();
+            if (ratio == 8 && n1 > 0) fa.a2_hist_new = f2->h.re[f2->h.cur ^ 1].as<float>();
+        } else {
+            fa.dem_out = ch->dem.p();
+            fa.a1_out = ch->a1.p();
+        }
         cudaError_t e = fm_tail_launch(fa, ch->exact, c->stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused FM kernel");
-        // the delay lines of the three filters slide in one launch; counters like FirFilter.filter leaves them
-        ChainStateArgs sa{};
-        auto line = [&](int i, rfa_fir *f, const float *in_re, const float *in_im, long long n) {
-            ChainStateArgs::Line &l = sa.line[i];
-            l.in_re = in_re;
-            l.in_im = in_im;
-            l.old_re = f->h.re[f->h.cur].as<float>();
-            l.old_im = in_im ? f->h.im[f->h.cur].as<float>() : nullptr;
-            l.new_re = f->h.re[f->h.cur ^ 1].as<float>();
-            l.new_im = in_im ? f->h.im[f->h.cur ^ 1].as<float>() : nullptr;
-            l.n = n;
-            l.hist = n > 0 ? f->h.hist : 0;
-        };
-        line(0, u, ch->q_re.p(), ch->q_im.p(), nq);
-        line(1, f1, ch->dem.p(), nullptr, ratio >= 2 ? nu : 0);
-        line(2, f2, ch->a1.p(), nullptr, ratio == 8 ? n1 : 0);
-        e = chain_state_launch(sa, c->stream);
-        if (e != cudaSuccess) return cuda_fail(e, "chain state kernel");
-        c->launches += nu > 0 ? 2 : 1;
+        if (!fused_state) {  // a call too short for a single demodulated sample: only delay lines move
+            ChainStateArgs sa{};
+            auto line = [&](int i, rfa_fir *f, const float *in_re, const float *in_im, long long n) {
+                ChainStateArgs::Line &l = sa.line[i];
+                l.in_re = in_re;
+                l.in_im = in_im;
+                l.old_re = f->h.re[f->h.cur].as<float>();
+                l.old_im = in_im ? f->h.im[f->h.cur].as<float>() : nullptr;
+                l.new_re = f->h.re[f->h.cur ^ 1].as<float>();
+                l.new_im = in_im ? f->h.im[f->h.cur ^ 1].as<float>() : nullptr;
+                l.n = n;
+                l.hist = n > 0 ? f->h.hist : 0;
+            };
+            line(0, u, ch->q_re.p(), ch->q_im.p(), nq);
+            line(1, f1, ch->dem.p(), nullptr, ratio >= 2 ? nu : 0);
+            line(2, f2, ch->a1.p(), nullptr, ratio == 8 ? n1 : 0);
+            e = chain_state_launch(sa, c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "chain state kernel");
+        }
+        c->launches += 1;
         if (nq > 0) u->h.cur ^= 1;
         u->first = u->first + nu * u->dec - nq;
         if (nu > 0) ch->carry_cur ^= 1;

@@ -65,10 +65,33 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
     __shared__ float s_a1[(TILE + HALO) / 2 + 2];                       // first decimator output
     __shared__ __align__(16) float s_tu[UT];
     __shared__ float s_t1[16], s_t2[16];
+    if (a.slide_user && blockIdx.x == gridDim.x - 1) {  // the extra CTA: the user filter's next delay line
+        const ChainStateArgs::Line &l = a.user_line;
+        for (int h = threadIdx.x; h < l.hist; h += blockDim.x) {
+            const long long k = l.n - l.hist + h;
+            float r = 0.0f, q = 0.0f;
+            if (k >= 0) {
+                r = l.in_re[k];
+                q = l.in_im[k];
+            } else if (k + l.hist >= 0) {
+                r = l.old_re[k + l.hist];
+                q = l.old_im[k + l.hist];
+            }
+            l.new_re[h] = r;
+            l.new_im[h] = q;
+        }
+        return;
+    }
     const long long u0 = (long long)blockIdx.x * TILE;                  // first demodulator index this CTA owns
     long long u1 = u0 + TILE;
     if (u1 > a.nu) u1 = a.nu;
     if (u0 >= u1) return;
+    if (blockIdx.x == 0) {  // calls shorter than a decimator's delay line keep the newest of the old one
+        if (a.a1_hist_new)
+            for (int h = threadIdx.x; h < a.a1_hist - a.nu; h += blockDim.x) a.a1_hist_new[h] = a.hist_a1[a.nu + h];
+        if (a.a2_hist_new)
+            for (int h = threadIdx.x; h < a.a2_hist - a.n1; h += blockDim.x) a.a2_hist_new[h] = a.hist_a2[a.n1 + h];
+    }
     for (int t = threadIdx.x; t < UT; t += blockDim.x) s_tu[t] = t < a.user_taps ? a.taps_user[t] : 0.0f;
     if (threadIdx.x < a.a1_taps) s_t1[threadIdx.x] = a.taps_a1[threadIdx.x];
     if (threadIdx.x < a.a2_taps) s_t2[threadIdx.x] = a.taps_a2[threadIdx.x];
@@ -178,6 +201,7 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
             if (i >= u0) {
                 if (a.dem_out) a.dem_out[i] = d;
                 if (a.ratio == 1) a.audio[i] = d;
+                if (a.a1_hist_new && i >= a.nu - a.a1_hist) a.a1_hist_new[i - (a.nu - a.a1_hist)] = d;
             }
         } else if (i + a.a1_hist >= 0 && a.hist_a1) {
             d = a.hist_a1[i + a.a1_hist];  // demodulated samples of earlier calls: the first decimator's delay line
@@ -233,6 +257,7 @@ __global__ void __launch_bounds__(256) fm_tail_kernel(const FmTailArgs a) {
                     if (a.first_a1 + 2 * m >= u0 && m < a.n1) {
                         if (a.a1_out) a.a1_out[m] = v;
                         if (a.ratio == 2) a.audio[m] = v;
+                        if (a.a2_hist_new && m >= a.n1 - a.a2_hist) a.a2_hist_new[m - (a.n1 - a.a2_hist)] = v;
                     }
                 } else if (m + a.a2_hist >= 0 && a.hist_a2) {
                     v = a.hist_a2[m + a.a2_hist];  // first-decimator outputs of earlier calls: the second decimator's delay line
@@ -288,14 +313,15 @@ __global__ void chain_state_kernel(const ChainStateArgs a) {
 cudaError_t fm_tail_launch(const FmTailArgs &a, bool exact, cudaStream_t st) {
     if (a.nu <= 0) return cudaSuccess;
     if (a.user_taps > UT || a.user_taps < 1 || a.a1_taps > 9 || a.a2_taps > 13) return cudaErrorInvalidValue;
+    const unsigned extra = a.slide_user ? 1u : 0u;
     if (a.nu >= 2048LL * 512) {
-        const unsigned grid = (unsigned)((a.nu + 2047) / 2048);
+        const unsigned grid = (unsigned)((a.nu + 2047) / 2048) + extra;
         if (exact)
             pdl_launch(fm_tail_kernel<true, 2048>, grid, 256, 0, st, a);
         else
             pdl_launch(fm_tail_kernel<false, 2048>, grid, 256, 0, st, a);
     } else {
-        const unsigned grid = (unsigned)((a.nu + 511) / 512);
+        const unsigned grid = (unsigned)((a.nu + 511) / 512) + extra;
         if (exact)
             pdl_launch(fm_tail_kernel<true, 512>, grid, 256, 0, st, a);
         else

@@ -93,7 +93,22 @@ struct ResampleArgs {
     int tile;           // outputs per CTA
     int span_max;       // shared-memory capacity in samples
     float *out_re, *out_im;
+    // the delay line after this call (the last src.hist samples of old history ++ `consumed` inputs): written by CTA 0 of
+    // the tiled / stripe kernels before it starts on its tiles, instead of a history_kernel launch behind the resampler
+    float *hist_new_re, *hist_new_im;
+    long long consumed;
 };
+
+template <int KIND>
+__device__ __forceinline__ void slide_history(const ResampleArgs &a) {
+    if (blockIdx.x != 0 || !a.hist_new_re) return;
+    for (int h = threadIdx.x; h < a.src.hist; h += blockDim.x) {
+        float r, q;
+        fetch<KIND>(a.src, a.consumed - a.src.hist + h, r, q);
+        a.hist_new_re[h] = r;
+        a.hist_new_im[h] = q;
+    }
+}
 
 template <int KIND, bool EXACT>
 __global__ void __launch_bounds__(256) resample_kernel(const ResampleArgs a) {
@@ -398,6 +413,7 @@ template <int KIND, int M, int AMAX>
 __global__ void __launch_bounds__(256) resample_tiled_kernel(const ResampleTiledArgs ta) {
     pdl_trigger();  // the small kernels behind the resampler may be scheduled now (pdl.h); they wait for this grid to finish
     const ResampleArgs &a = ta.a;
+    slide_history<KIND>(a);
     constexpr int AP = (AMAX + 3) & ~3;
     extern __shared__ float2 xs[];  // [span_max + 8] samples, then the transposed bank [I][D][AP]
     float *hT = reinterpret_cast<float *>(xs + a.span_max + 8);
@@ -528,6 +544,7 @@ __device__ __forceinline__ void resample_stripe_body(const ResampleStripeArgs &s
     long long t_prev_ = clock64();
 #endif
     const ResampleArgs &a = sa.a;
+    slide_history<KIND>(a);
     // shared memory: [2 + span_max + 8] samples (two entries of slack in front: a lane may look one sample back), the
     // NCO table [512], the bank as zero-padded rows [I][pad + nt + pad], reduction scratch, slot table
     extern __shared__ float2 smem_stripe[];
@@ -905,10 +922,13 @@ static StreamSrc make_src(const StreamDesc &d) {
 }
 
 cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int D, int nt, long long rel, int ph0,
-                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st, int rs_span) {
+                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st, int rs_span,
+                            float *hist_new_re, float *hist_new_im, long long consumed, bool *hist_done) {
+    if (hist_done) *hist_done = false;
     if (nout <= 0) return cudaSuccess;
     if (nt + 2 > kSpanMax) return cudaErrorInvalidValue;
     ResampleArgs a{};
+    const bool want_hist = hist_done && hist_new_re && hist_new_im && in.hist > 0 && consumed > 0;
     a.src = make_src(in);
     a.bank = bank;
     a.I = I;
@@ -938,6 +958,11 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
         if (tpc >= TP) {
             ResampleStripeArgs sa{};
             sa.a = a;
+            if (want_hist) {
+                sa.a.hist_new_re = hist_new_re;
+                sa.a.hist_new_im = hist_new_im;
+                sa.a.consumed = consumed;
+            }
             sa.TPC = (int)tpc;
             sa.pad = (int)(((long long)(PH - 1) * D + I - 1) / I) + 1 + 68;
             sa.a.tile = (int)(tpc * I);
@@ -990,6 +1015,7 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
                     if (pass == 0) sonce.done(sdev);
                 }
 #undef RFA_STRIPE
+                if (want_hist) *hist_done = true;
                 return cudaGetLastError();
             }
         }
@@ -1006,6 +1032,11 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
         if (B >= 1) {
             ResampleTiledArgs ta{};
             ta.a = a;
+            if (want_hist) {
+                ta.a.hist_new_re = hist_new_re;
+                ta.a.hist_new_im = hist_new_im;
+                ta.a.consumed = consumed;
+            }
             ta.a.span_max = kSpanT;
             ta.a.tile = (int)((long long)I * M * B);
             ta.B = (int)B;
@@ -1062,6 +1093,7 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
             }
 #undef RFA_RT_ALL
 #undef RFA_RT
+            if (want_hist) *hist_done = true;
             return cudaGetLastError();
         }
     }

@@ -21,8 +21,12 @@ struct StreamDesc {
     const float *nco_cos = nullptr, *nco_sin = nullptr;  // device tables; nullptr = no mixing
     int nco_len = 1, nco_idx = 0;
 };
+// hist_new_* / consumed / hist_done: the delay line after the call; *hist_done = true when the resampler kernel wrote it
+// itself (tiled and stripe kernels), false when the caller still has to launch history_launch
 cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int D, int nt, long long rel, int ph0,
-                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st, int rs_span = 0);
+                            long long nout, float *out_re, float *out_im, bool exact, cudaStream_t st, int rs_span = 0,
+                            float *hist_new_re = nullptr, float *hist_new_im = nullptr, long long consumed = 0,
+                            bool *hist_done = nullptr);
 cudaError_t fir_launch(const StreamDesc &in, const float *taps_re, const float *taps_im, int ntaps, int dec,
                        long long first, long long nout, bool real_only, float *out_re, float *out_im, bool exact,
                        cudaStream_t st);
@@ -33,6 +37,17 @@ cudaError_t demod_power_launch(const float *re, const float *im, long long n, fl
                                cudaStream_t st);
 cudaError_t agc_launch(float *x, const long long *off, int npackets, long long max_packet, bool subtract_mean,
                        float *state, float *scratch, float volume, bool exact, int num_sms, cudaStream_t st);
+
+// the delay lines of the user filter and both decimators slide in one launch
+struct ChainStateArgs {
+    struct Line {
+        const float *in_re, *in_im, *old_re, *old_im;
+        float *new_re, *new_im;
+        long long n;  // inputs of this call
+        int hist;     // 0 = unused
+    } line[3];
+};
+cudaError_t chain_state_launch(const ChainStateArgs &a, cudaStream_t st);
 
 // everything behind the resampler of an FM chain in one launch (chain_fused.cu)
 struct FmTailArgs {
@@ -52,18 +67,14 @@ struct FmTailArgs {
     long long first_a1, first_a2, n1, n2;
     float *dem_out, *a1_out;               // intermediates kept for the next call's delay lines (may be NULL when unused)
     float *audio;                          // 48 kHz audio of this call
+    // the call's bookkeeping inside the same launch (no chain_state_kernel behind it): one extra CTA slides the user
+    // filter's delay line, the CTAs that own the newest demodulated / first-decimator samples write the decimators' next
+    // delay lines (NULL: that decimator is not in the chain or saw no input)
+    int slide_user;                        // 1: grid has one extra CTA for user_line
+    ChainStateArgs::Line user_line;
+    float *a1_hist_new, *a2_hist_new;
 };
 cudaError_t fm_tail_launch(const FmTailArgs &a, bool exact, cudaStream_t st);
-// the delay lines of the user filter and both decimators slide in one launch
-struct ChainStateArgs {
-    struct Line {
-        const float *in_re, *in_im, *old_re, *old_im;
-        float *new_re, *new_im;
-        long long n;  // inputs of this call
-        int hist;     // 0 = unused
-    } line[3];
-};
-cudaError_t chain_state_launch(const ChainStateArgs &a, cudaStream_t st);
 
 // everything behind the resampler of an AM / SSB / CW chain in three launches (chain_agc.cu, RFA_SUM_FMA)
 struct AgcTailArgs {

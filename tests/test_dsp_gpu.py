@@ -339,6 +339,35 @@ def test_fused_agc_tail_streams_across_calls(gpu_ctx, oracle, fmt, fs, mode, wid
     assert np.abs(got[ok] - want[ok]).max() <= 1e-4 * np.abs(want[ok]).max()
 
 
+@pytest.mark.parametrize("fmt,fs,mode,width,packet,calls,exact", [
+    (1, 2_400_000, 3, 100_000, 8192, (5, 1, 6), False),       # wFM: tiled resampler, both decimators
+    (2, 10_000_000, 2, 10_000, 65536, (2, 1, 3), False),      # nFM: stripe resampler, first decimator
+    (1, 2_400_000, 3, 100_000, 16, (3, 40, 1, 2, 60), False), # wFM, calls of two or three quadrature samples
+    (1, 2_400_000, 2, 10_000, 64, (2, 30, 1, 50), True),      # nFM exact, calls shorter than the decimator's delay line
+])
+def test_fm_chain_streams_across_calls_with_in_kernel_delay_lines(gpu_ctx, oracle, fmt, fs, mode, width, packet, calls, exact):
+    """The FM chain's delay lines (resampler, user filter, both audio decimators) slide inside the resampler and FM
+    tail kernels: several calls of uneven length -- some shorter than a decimator's delay line -- equal the oracle's
+    single run."""
+    import rfanalyzer_b200 as rfa
+    n = packet * sum(calls)
+    iq, src, chan = _chain_input(oracle, rfa, fmt, fs, mode, n)
+    want = oracle.chain_run(fmt, iq, fs, src, chan, mode, width, packet, volume=0.8)
+    plan = rfa.ChainPlan(gpu_ctx, fmt, fs, src, chan, mode, width, packet, 0.8, rfa.SUM_EXACT if exact else rfa.SUM_FMA)
+    bps = 2 if fmt < 2 else 4
+    got, pos = [], 0
+    for k in calls:
+        m = packet * k
+        audio = np.zeros(plan.max_audio(m), np.float32)
+        cnt = plan.process(iq[pos * bps:(pos + m) * bps], m, audio)
+        got.append(audio[:cnt])
+        pos += m
+    got = np.concatenate(got)
+    assert len(got) == len(want)
+    peak = np.abs(want).max()
+    assert np.abs(got - want).max() <= (1e-6 if exact else 1e-4) * peak
+
+
 def test_chain_device_buffers(gpu_ctx, oracle):
     import torch
     import rfanalyzer_b200 as rfa
