@@ -583,7 +583,9 @@ class ChainPlan:
         return n.value
 
     def process(self, iq, nsamples, audio):
-        """audio: float32 buffer of at least max_audio(nsamples); returns the number of samples written."""
+        """audio: float32 buffer of at least max_audio(nsamples); returns the number of samples written.
+        Host arrays: the audio is there on return.  Device tensors: the call only enqueues work on the context's
+        stream (the count is exact on return); synchronise the context or keep working on that stream."""
         n = C.c_longlong()
         from .engine import _mem_of
         cap = audio.numel() if hasattr(audio, "numel") else len(audio)
