@@ -350,6 +350,11 @@ static int process_piece(rfa_scheduler *s, const void *packets, long long npacke
         }
         if (int rc = run_chain(dem)) return rc;
     }
+    if (demod && mem == RFA_MEM_DEVICE) {
+        // device-buffer chain calls only enqueue work on the chain's own stream: the call returns with the audio written
+        RFA_CK(cudaEventRecord(s->ev, s->ctx2->stream));
+        RFA_CK(cudaStreamWaitEvent(c->stream, s->ev, 0));
+    }
     RFA_CK(cudaStreamSynchronize(c->stream));
     s->fill = fill;
     s->packets_total += npackets;
