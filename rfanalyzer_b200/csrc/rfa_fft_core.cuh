@@ -339,13 +339,16 @@ struct Dft<32> {
 // ---------------------------------------------------------------------------
 // Radix plan of an n-point transform, shared by the kernels (Plan<NL>) and the host table builder
 // (make_pass_twiddles): as many radix-16 passes as fit, then one radix-2/4/8 pass -- except for
-// 16384 points, where a thread holds 32 points and 16 x 32 x 32 saves a whole pass (and exchange).
+// 8192 and 16384 points, where a thread holds 32 points and 16 x 16 x 32 / 16 x 32 x 32 save a whole pass (and exchange).
 #ifdef RFA_R8  // timing experiment: N = 4096 as 8 x 8 x 8 x 8 with 8 points per thread (512 threads per frame, <= 64 registers)
 RFA_CX int plan_passes(int lg) { return lg == 12 ? 4 : (lg == 14 ? 3 : lg / 4 + (lg % 4 ? 1 : 0)); }
 RFA_CX int plan_radix(int lg, int pass) {
     return lg == 12 ? 8 : (lg == 14 ? (pass == 0 ? 16 : 32) : (pass < lg / 4 ? 16 : (1 << (lg % 4))));
 }
-#elif defined(RFA_E32_8192)  // timing experiment: N = 8192 as 16 x 16 x 32 with 32 points per thread (256 threads per frame, two CTAs per SM)
+#elif !defined(RFA_8192_T512)
+// N = 8192 is 16 x 16 x 32 with 32 points per thread as well: 256 threads per frame and ONE exchange frame let two CTAs
+// share an SM (53.9 against 57.2 us per 2^24 int8 samples for 16 x 16 x 16 x 2 on one 512-thread CTA,
+// profiles/r02p_8192_e32_and_average_cta.txt; -DRFA_8192_T512 builds the earlier geometry)
 RFA_CX int plan_passes(int lg) { return (lg == 14 || lg == 13) ? 3 : lg / 4 + (lg % 4 ? 1 : 0); }
 RFA_CX int plan_radix(int lg, int pass) {
     return lg == 14 ? (pass == 0 ? 16 : 32) : (lg == 13 ? (pass < 2 ? 16 : 32) : (pass < lg / 4 ? 16 : (1 << (lg % 4))));

@@ -58,7 +58,7 @@ template <int NL>
 struct Geom {
 #ifdef RFA_R8
     static constexpr int T = NL == 4096 ? 512 : (NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1)));
-#elif defined(RFA_E32_8192)
+#elif !defined(RFA_8192_T512)
     static constexpr int T = NL == 8192 ? 256 : (NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1)));
 #else
     static constexpr int T = NL >= 8192 ? 512 : (NL >= 16 * 16 ? NL / 16 : (NL / 16 > 0 ? NL / 16 : 1));
@@ -67,7 +67,7 @@ struct Geom {
     static constexpr int FPC = T >= 256 ? 1 : 256 / T;   // frames per CTA
     static constexpr int CTA = T * FPC;
     // two ping-pong frames per slot (one barrier per pass) while they fit comfortably
-#ifdef RFA_E32_8192
+#ifndef RFA_8192_T512
     static constexpr int NBUF = NL < 8192 ? 2 : 1;
 #else
     static constexpr int NBUF = NL <= 8192 ? 2 : 1;
