@@ -514,7 +514,8 @@ struct ResampleStripeArgs {
     int TPC;         // periods per CTA (a multiple of TP)
     int pad;         // zero taps on either side of a bank row in shared memory
     int raw_bytes;   // shared-memory room for the next tile's raw codes (0: no bulk-copy staging)
-    int acc_pairs;   // I * TPC rounded up to an even count: per-output accumulators in front of the samples
+    int acc_pairs;   // accumulators in front of the samples: one float pair per output AND per warp that shares a task's sample range
+    int part_pairs;  // I * TPC rounded up to an even count: the accumulators of one such warp ("part")
     int nco_pairs;   // room for the (cos, sin) table
 };
 
@@ -777,7 +778,9 @@ __device__ __forceinline__ void resample_stripe_body(const ResampleStripeArgs &s
         if (lane < PH * TP * 2) {
             const int v = lane;
             const int s = (v >> 1) / TP, q = (v >> 1) % TP;
-            if (s0 + s < a.I) atomicAdd(&s_acc[(((pi0 + q) * a.I) + s0 + s) * 2 + (v & 1)], vals[0]);
+            // every part keeps its own copy (no atomics: the parts are added in a fixed order below, so the result does not
+            // depend on which warp arrives first)
+            if (s0 + s < a.I) s_acc[(size_t)part * 2 * sa.part_pairs + (((pi0 + q) * a.I) + s0 + s) * 2 + (v & 1)] = vals[0];
         }
         __syncwarp();
     }
@@ -785,10 +788,12 @@ __device__ __forceinline__ void resample_stripe_body(const ResampleStripeArgs &s
     for (int i = threadIdx.x; i < 2 * a.tile; i += blockDim.x) {  // tile outputs: period-major, phase slot, (re, im)
         const long long j = j0 + (i >> 1);
         if (j < a.nout) {
+            float v = s_acc[i];
+            for (int part = 1; part < nsplit; part++) v += s_acc[(size_t)part * 2 * sa.part_pairs + i];
             if (i & 1)
-                a.out_im[j] = s_acc[i];
+                a.out_im[j] = v;
             else
-                a.out_re[j] = s_acc[i];
+                a.out_re[j] = v;
         }
     }
     STRIPE_STAMP(5);  // dot products (warp 0's tasks)
@@ -974,7 +979,8 @@ cudaError_t resample_launch(const StreamDesc &in, const float *bank, int I, int 
             const bool variant_b = rs_span == 2;
             const bool variant_d = rs_span != 1 && rs_span != 2;  // the default; knob rs_span = 1: eight warps per CTA (97 registers)
             const int warps = (variant_b || variant_d) ? 12 : 8;
-            sa.acc_pairs = (int)((tpc * I + 1) & ~1LL);
+            sa.part_pairs = (int)((tpc * I + 1) & ~1LL);
+            sa.acc_pairs = sa.part_pairs * (tasks < warps ? warps / tasks : 1);  // the kernel's nsplit
             sa.raw_bytes = (variant_b && in.kind <= 2) ? (int)(((size_t)sa.a.span_max * (in.kind == 2 ? 4 : 2) + 15) & ~(size_t)15) : 0;
             sa.nco_pairs = in.nco_cos ? ((in.nco_len + 1 + 7) & ~7) : 8;  // one entry more than the table: its entry 0 again
             const size_t ssmem = ((size_t)sa.a.span_max + 10 + sa.nco_pairs + sa.acc_pairs) * sizeof(float2) + (size_t)I * (nt + 2 * sa.pad) * sizeof(float) +
