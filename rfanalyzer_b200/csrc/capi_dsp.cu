@@ -444,9 +444,6 @@ struct rfa_chain {
     long long agc_tab_npk = 0, agc_tab_used[2] = {0, 0};
     int agc_tab_cur = 0;
     int agc_cur = 0;             // which of the two agc_state floats holds lastMax
-    Buf seg_pin[4];              // pinned staging slots of the packet-boundary table
-    cudaEvent_t seg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    unsigned long long seg_calls = 0;
     DevF q_re, q_im, u_re, u_im, b_re, b_im, dem, a1, a2;
     Buf s_iq, s_audio;
     // rfa_chain_process advances the streaming state stage by stage; a failure in the middle of a call leaves
@@ -476,10 +473,6 @@ int rfa_chain_destroy(rfa_chain *ch) {
     rfa_fir_destroy(ch->audio1);
     rfa_fir_destroy(ch->audio2);
     for (Buf *b : {&ch->nco, &ch->fm_carry, &ch->agc_state, &ch->agc_scratch, &ch->seg, &ch->s_iq, &ch->s_audio, &ch->agc_tab}) b->release();
-    for (int i = 0; i < 4; i++) {
-        ch->seg_pin[i].release();
-        if (ch->seg_ev[i]) cudaEventDestroy(ch->seg_ev[i]);
-    }
     for (DevF *f : {&ch->q_re, &ch->q_im, &ch->u_re, &ch->u_im, &ch->b_re, &ch->b_im, &ch->dem, &ch->a1, &ch->a2}) f->b.release();
     delete ch;
     return RFA_OK;
@@ -703,6 +696,34 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
     }
     const long long nq = q_off[npk], nu = u_off[npk], nb = b_off[npk];
 
+    // ---- AM / SSB / CW, RFA_SUM_FMA: the packet boundaries of the demodulated stream go to the device in closed form,
+    // by a one-thread-per-packet kernel in FRONT of the resampler (the kernels behind it then follow each other with no
+    // copy in between).  The closed form must reproduce the per-packet loop above, boundary for boundary.
+    bool packet_table_ready = false;
+    if (!ch->exact && mode != RFA_MODE_NFM && mode != RFA_MODE_WFM && ch->user->dec == 1) {
+        const bool am = mode == RFA_MODE_AM;
+        PacketMap pm{};
+        pm.packet_samples = P;
+        pm.nsamples = nsamples;
+        pm.rel = ch->rs->rel;
+        pm.ph = ch->rs->ph;
+        pm.I = ch->rs->I;
+        pm.D = ch->rs->D;
+        pm.first_u = ch->user->first;
+        pm.first_b = am ? 0 : ch->band->first;
+        pm.dec_b = am ? 0 : ch->band->dec;
+        pm.npk = (int)npk;
+        const std::vector<long long> &want = am ? u_off : b_off;
+        for (long long p = 0; p <= npk; p++)
+            RFA_REQUIRE(pm.off(p) == want[(size_t)p], "internal: packet boundary %lld in closed form (%lld) differs from the "
+                        "per-packet count (%lld)", p, pm.off(p), want[(size_t)p]);
+        if (int rc = ch->seg.ensure((size_t)(npk + 1) * sizeof(long long))) return rc;
+        cudaError_t e = packet_table_launch(pm, ch->seg.as<long long>(), c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "packet table kernel");
+        c->launches++;
+        packet_table_ready = true;
+    }
+
     // ---- K2+K4: convert, mix and resample to the quadrature rate ------------------------------
     if (int rc = ch->q_re.ensure(nq)) return rc;
     if (int rc = ch->q_im.ensure(nq)) return rc;
@@ -858,7 +879,7 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
             ta.hist_b_re = b->h.re[b->h.cur].as<float>();
             ta.hist_b_im = b->h.im[b->h.cur].as<float>();
         }
-        if (u->dec == 1 && (ratio == 1 || ratio == 2) && (ratio == 1 || f1->ntaps <= 9) && agc_tail_supported(ta)) {
+        if (packet_table_ready && (ratio == 1 || ratio == 2) && (ratio == 1 || f1->ntaps <= 9) && agc_tail_supported(ta)) {
             const long long n1 = ratio == 2 ? f1->count(nx) : 0;
             const long long nfinal = ratio == 2 ? n1 : nx;
             RFA_REQUIRE(nfinal <= capacity, "internal: audio count %lld exceeds capacity %lld", nfinal, capacity);
@@ -884,21 +905,6 @@ int rfa_chain_process(rfa_chain *ch, const void *iq, long long nsamples, float *
             double *sum_next = ch->agc_tab.as<double>() + (size_t)(tcur ^ 1) * ch->agc_tab_npk;
             unsigned *mx_base = reinterpret_cast<unsigned *>(ch->agc_tab.as<double>() + 2 * (size_t)ch->agc_tab_npk);
             unsigned *mx_enc = mx_base + (size_t)tcur * ch->agc_tab_npk, *mx_next = mx_base + (size_t)(tcur ^ 1) * ch->agc_tab_npk;
-            // packet boundaries: through one of four pinned slots, so that neither the copy nor the call waits for the host
-            {
-                const int slot = (int)(ch->seg_calls++ & 3);
-                if (!ch->seg_ev[slot])
-                    RFA_CK(cudaEventCreateWithFlags(&ch->seg_ev[slot], cudaEventDisableTiming));
-                else
-                    RFA_CK(cudaEventSynchronize(ch->seg_ev[slot]));
-                ch->seg_pin[slot].pinned = true;
-                const size_t bytes = (size_t)(npk + 1) * sizeof(long long);
-                if (int rc = ch->seg_pin[slot].ensure(bytes)) return rc;
-                if (int rc = ch->seg.ensure(bytes)) return rc;
-                memcpy(ch->seg_pin[slot].p, (am ? u_off : b_off).data(), bytes);
-                RFA_CK(cudaMemcpyAsync(ch->seg.p, ch->seg_pin[slot].p, bytes, cudaMemcpyHostToDevice, c->stream));
-                RFA_CK(cudaEventRecord(ch->seg_ev[slot], c->stream));
-            }
             float *d_audio = audio;
             if (mem == RFA_MEM_HOST) {
                 if (int rc = ch->a2.ensure(nfinal)) return rc;

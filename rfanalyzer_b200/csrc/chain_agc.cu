@@ -9,7 +9,7 @@
 //                     call's bookkeeping (delay lines, table of the next call)
 // Round 1 ran this as nine to ten launches (two FIR kernels with a history kernel each, power, packet statistics, scan,
 // normalise, audio decimator + history, a device copy) behind a host-synchronised segment upload: 55 us per 2^24-sample
-// call for 1.6e5 quadrature samples.  Here a CTA of the first kernel owns a run of TILE demodulated samples: it stages the
+// call for 1.6e5 quadrature samples.  (The packet boundaries now come from packet_table_kernel, in closed form.)  Here a CTA of the first kernel owns a run of TILE demodulated samples: it stages the
 // quadrature samples that run needs, runs the user filter into shared memory (de-interleaved by the band filter's
 // decimation phase), the band-pass out of shared memory, and adds its packets' maxima to the call's table with one atomic
 // per packet and warp.  The 181-tap complex band-pass was bound by shared-memory wavefronts (a tap and a sample load per
@@ -451,7 +451,20 @@ __global__ void __launch_bounds__(256) agc_apply_kernel(const AgcApplyArgs a) {
     }
 }
 
+// the call's packet boundaries, one thread per packet (launched BEFORE the resampler: the three kernels behind it then
+// follow each other without a copy in between)
+__global__ void packet_table_kernel(const PacketMap pm, long long *off) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p <= pm.npk) off[p] = pm.off(p);
+}
+
 }  // namespace
+
+cudaError_t packet_table_launch(const PacketMap &pm, long long *off, cudaStream_t st) {
+    if (pm.npk < 0) return cudaErrorInvalidValue;
+    packet_table_kernel<<<(unsigned)((pm.npk + 1 + 255) / 256), 256, 0, st>>>(pm, off);
+    return cudaGetLastError();
+}
 
 bool agc_tail_supported(const AgcTailArgs &a) {
     if (a.nx <= 0 || a.user_taps < 1 || a.user_taps > UT || a.npk < 1) return false;

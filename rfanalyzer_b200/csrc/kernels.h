@@ -76,6 +76,36 @@ struct FmTailArgs {
 };
 cudaError_t fm_tail_launch(const FmTailArgs &a, bool exact, cudaStream_t st);
 
+// Packet boundaries of a chain call in the demodulated stream, in closed form: the resampler emits output j at input
+// position rel + floor((ph + j*D)/I), a decimating filter emits at inputs first + m*dec, so the outputs that exist after n
+// inputs are counts of those positions below n -- the same numbers the per-packet loop of rfa_chain_process accumulates
+// (it checks them against each other).  off(p) = demodulated samples before packet p; off(npk) = all of the call.
+struct PacketMap {
+    long long packet_samples, nsamples;
+    long long rel;            // resampler state before the call
+    int ph, I, D;
+    long long first_u;        // user filter (decimation 1)
+    long long first_b;        // band-pass (dec_b > 0) behind it
+    int dec_b;                // 0: none (AM)
+    int npk;
+#if defined(__CUDACC__)
+    __host__ __device__
+#endif
+    long long off(long long p) const {
+        long long n = p * packet_samples;
+        if (n > nsamples) n = nsamples;
+        long long q = 0;
+        if (n > rel) {
+            const long long num = (n - rel) * I - ph;
+            q = (num + D - 1) / D;
+        }
+        long long u = q > first_u ? q - first_u : 0;
+        if (dec_b > 0) u = u > first_b ? (u - 1 - first_b) / dec_b + 1 : 0;
+        return u;
+    }
+};
+cudaError_t packet_table_launch(const PacketMap &pm, long long *off /* [npk + 1], device */, cudaStream_t st);
+
 // everything behind the resampler of an AM / SSB / CW chain in three launches (chain_agc.cu, RFA_SUM_FMA)
 struct AgcTailArgs {
     const float *q_re, *q_im;              // quadrature samples of this call
