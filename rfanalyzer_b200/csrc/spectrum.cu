@@ -57,31 +57,21 @@ __global__ void average_rows_kernel(const float *rows, long long newest, long lo
     // chained by programmatic dependent launch between the four-step row kernel and the next call's column kernel
     launch_dependents();
     grid_dependency_wait();
-    // where the newest L+1 rows start: once per CTA; then every load of a bin is in flight before the first one is added
-    // (a loop of dependent modulo + load + add made this kernel nine L2 round trips long, on the critical path between the
-    // row kernel and the next call's column kernel)
-    __shared__ long long s_row_off[31];
-    if (threadIdx.x < 31) {
-        long long row = newest + (long long)threadIdx.x * dir;
-        if (ring_rows > 0) {
-            row %= ring_rows;
-            if (row < 0) row += ring_rows;
-        }
-        s_row_off[threadIdx.x] = row * row_stride;
-    }
-    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    float v[31];
-#pragma unroll
-    for (int r = 0; r < 31; r++) {
-        v[r] = -9999.0f;
-        if (r <= L && r < valid) v[r] = rows[s_row_off[r] + i];
-    }
     float sum = 0.0f;
-#pragma unroll
-    for (int r = 0; r < 31; r++)
-        if (r <= L) sum = __fadd_rn(sum, v[r]);
+    for (int r = 0; r <= L; r++) {
+        float v = -9999.0f;
+        if (r < valid) {
+            long long row = newest + (long long)r * dir;
+            if (ring_rows > 0) {
+                row %= ring_rows;
+                if (row < 0) row += ring_rows;
+            }
+            v = rows[row * row_stride + i];
+        }
+        sum = __fadd_rn(sum, v);
+    }
     avg[i] = __fdiv_rn(sum, (float)(L + 1));
 }
 void average_rows(const float *rows, long long newest, long long dir, long long ring_rows, long long row_stride,
