@@ -187,13 +187,18 @@ struct SpectrumFrame {
     }
 
     // phase 0 (non-prefetching formats and split transforms): gather + convert + window + fold
+    template <bool SH = false>
     static RFA_HD void first(const SpectrumParams &p, long long f, int c, int tid, const float *wreg, cf *u,
                              const char *staged = nullptr) {
         constexpr int R = PL::radix(0);
         constexpr int NB = E / R, STR = NL / R;
         // one 64-bit address per frame; every point of this thread is a constant offset from it
         // (`staged`: the frame's raw codes in shared memory instead -- STAGED kernels with 32 points per thread)
-        const char *src = (staged ? staged : (const char *)p.in + f * (long long)N * in_elem_bytes<IN>()) + (size_t)tid * in_elem_bytes<IN>();
+        // SH: the frame's raw codes sit in shared memory (`staged`); the compiler is told so, or the loads are generic LDs
+        const char *src = (SH ? staged : (const char *)p.in + f * (long long)N * in_elem_bytes<IN>()) + (size_t)tid * in_elem_bytes<IN>();
+#ifdef __CUDA_ARCH__
+        if constexpr (SH) __builtin_assume(__isShared(src));
+#endif
         const float *src_im = (IN == FMT_PF32) ? p.in_im + (f * (long long)N + tid) : nullptr;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
@@ -745,7 +750,7 @@ __global__ void __launch_bounds__(Geom<NL>::CTA, Geom<NL>::CTA <= 256 ? RFA_MINC
                     F::load_raw((const char *)(stage + sb * CHUNK_BYTES) + ((f - f0) * (long long)NL + tid) * BPS, raw);
                     F::first_from_raw(raw, wreg, u);
                 } else {  // 32 points per thread: convert straight out of the staged chunk
-                    F::first(p, f, c, tid, wreg, u, (const char *)(stage + sb * CHUNK_BYTES) + (f - f0) * (long long)NL * BPS);
+                    F::template first<true>(p, f, c, tid, wreg, u, (const char *)(stage + sb * CHUNK_BYTES) + (f - f0) * (long long)NL * BPS);
                 }
             }
             const int q_refill = NSTG == 2 ? q_next2 : q_next;
